@@ -1,0 +1,384 @@
+// lbm3d_kernels.cuh -- sm_100a kernels of the D3Q19 cavity hot path (fp64, bit-exact vs the reference).
+//
+// Reference path: /root/reference/3D Lid-driven Cavity with Lattice Boltzmann Method/main.c ("3D:")
+//   macrocollideandstream 3D:215-321, HechtBC 3D:385-675, diff 3D:678-685, macrovars 3D:695-719,
+//   calcvmag 3D:730-738, calcfeq/checkfeq 3D:163-169, 687-692.
+//
+// Formulation (DESIGN.md "Kernels"): ONE fused pull kernel per time step.  The lattice in HBM
+// holds POST-collision populations S; a thread owns one cell x and
+//   1. gathers F_q = S_old[x - c_q][q]            (what the reference's push streaming delivers),
+//      w[q] where the source lies outside the box (slots the reference never writes),
+//   2. applies the cell-local wall / lid / edge / corner rule of x's boundary class (d3q19_rules.h),
+//      -> F is now bit-identical to the reference's f2[x][:] after HechtBC,
+//   3. collides (BGK or TRT) in the reference's operation order and stores S_new[x][:] -- 19 aligned,
+//      coalesced 8-byte stores; 19 loads, 19 stores, 304 algorithmic bytes per cell update.
+// No tensor cores: the work is a stencil, not a contraction.  Compile with -fmad=false: FMA
+// contraction changes the bits.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "d3q19_rules.h"
+
+namespace lbm3d {
+
+constexpr int Q = 19;
+// 3D:31-33
+#define LBM_W0 (1.0 / 3.0)
+#define LBM_W1 (1.0 / 18.0)
+#define LBM_W2 (1.0 / 36.0)
+
+// X(q, cx, cy, cz, weight) -- velocities 3D:36-38, weights 3D:35
+#define LBM_D3Q19_VEL(X)                                                                             \
+    X(0, 0, 0, 0, LBM_W0)                                                                            \
+    X(1, 1, 0, 0, LBM_W1) X(2, -1, 0, 0, LBM_W1) X(3, 0, 1, 0, LBM_W1) X(4, 0, -1, 0, LBM_W1)        \
+    X(5, 0, 0, 1, LBM_W1) X(6, 0, 0, -1, LBM_W1)                                                     \
+    X(7, 1, 1, 0, LBM_W2) X(8, -1, -1, 0, LBM_W2) X(9, 1, 0, 1, LBM_W2) X(10, -1, 0, -1, LBM_W2)     \
+    X(11, 0, 1, 1, LBM_W2) X(12, 0, -1, -1, LBM_W2) X(13, 1, -1, 0, LBM_W2) X(14, -1, 1, 0, LBM_W2)  \
+    X(15, 1, 0, -1, LBM_W2) X(16, -1, 0, 1, LBM_W2) X(17, 0, 1, -1, LBM_W2) X(18, 0, -1, 1, LBM_W2)
+
+enum Mode : int {
+    MODE_STEP = 0,              // gather + BC + collide + store S_new
+    MODE_STEP_STOREF = 1,       // ... and also store F (the reference's f2) to the F buffer
+    MODE_STEP_DIFF_STOREF = 2,  // ... and accumulate sum (F - Fbuf)^2 before overwriting Fbuf
+    MODE_MATERIALISE = 3        // gather + BC, store F only (no collide, no state change)
+};
+
+// Kernel parameters (passed by value; lives in the constant bank).
+struct KP {
+    const double *src;   // S_old, population stride PS, plane -1 (ghost) first
+    double *dst;         // S_new, same layout
+    double *Fbuf;        // F buffer [q][nzl*N2] (no ghosts), may be null for MODE_STEP
+    const double *side_rd;  // stale f14 of the x=N-1 face, [nzl][N] (written two iterations ago)
+    double *side_wr;        // slot this iteration writes
+    double *partials;    // per-block partial sums (MODE_STEP_DIFF_STOREF)
+    int *flag;           // sticky negative-feq flag
+    int N, M;            // grid points per side, N-1
+    int Mz;              // global N-1 along z
+    int nzl, k0;         // owned planes, global index of local plane 0
+    int kl0, kstride;    // this launch covers local planes kl0 + blockIdx.z * kstride
+    int partial_base;    // offset of this launch's block partials
+    long long N2, PS, FS;
+    double omega, omegam, omomega, gammainv;   // 3D:21,23,30,40
+    double ulid, vlid, wlid, vfrac, third, sixth;  // 3D:183-191, 386, 41-42
+};
+
+// ---- collision --------------------------------------------------------------------------------
+// In place: f (pre-collision, the reference's f1[x][:]) -> post-collision f*.  Returns true if any
+// equilibrium was negative (checkfeq, 3D:687-692).
+//
+// Operation order follows 3D:224-246 (BGK) and 3D:268-302 (TRT) exactly; the only rewrites are
+// exact identities (no rounding changes): multiplying by c in {-1,0,1} becomes add/sub/skip;
+// cdotu(opp q) = -cdotu(q), so 3*cdotu and (4.5*cdotu^2 - 1.5*U2)*gammainv are shared by a pair;
+// w_q*rho has three distinct values; axis pairs reuse u*u, v*v, w*w from U2.
+template <int METHOD>
+__device__ __forceinline__ bool collide(double (&f)[Q], const KP &p) {
+    // 3D:268-270 / 3D:225-235 (the += loop visits q = 0..18: same order, zero terms are exact)
+    double rho = f[0] + f[1];
+    rho += f[2]; rho += f[3]; rho += f[4]; rho += f[5]; rho += f[6]; rho += f[7]; rho += f[8];
+    rho += f[9]; rho += f[10]; rho += f[11]; rho += f[12]; rho += f[13]; rho += f[14];
+    rho += f[15]; rho += f[16]; rho += f[17]; rho += f[18];
+    // 3D:272-281: x-moving 1,2,7,8,9,10,13,14,15,16; y: 3,4,7,8,11,12,13,14,17,18; z: 5,6,9,..,18
+    double us = f[1] - f[2];
+    us += f[7]; us -= f[8]; us += f[9]; us -= f[10]; us += f[13]; us -= f[14]; us += f[15]; us -= f[16];
+    double vs = f[3] - f[4];
+    vs += f[7]; vs -= f[8]; vs += f[11]; vs -= f[12]; vs -= f[13]; vs += f[14]; vs += f[17]; vs -= f[18];
+    double ws = f[5] - f[6];
+    ws += f[9]; ws -= f[10]; ws += f[11]; ws -= f[12]; ws -= f[15]; ws += f[16]; ws -= f[17]; ws += f[18];
+
+    double u, v, w;
+    if (METHOD == 1) {  // TRT multiplies by the reciprocal (3D:271-281)
+        const double rinv = 1.0 / rho;
+        u = us * rinv; v = vs * rinv; w = ws * rinv;
+    } else {            // BGK divides (3D:237-239)
+        u = us / rho; v = vs / rho; w = ws / rho;
+    }
+    const double uu = u * u, vv = v * v, ww = w * w;
+    const double U2 = (uu + vv) + ww;   // 3D:240, 284
+    const double k15 = 1.5 * U2;
+    const double wr0 = LBM_W0 * rho, wr1 = LBM_W1 * rho, wr2 = LBM_W2 * rho;  // `w * rho * (...)`, 3D:166
+    bool neg = false;
+
+    {   // rest population, cdotu = 0: feq = w*rho*(1.0 + (0 - 1.5*U2)*gammainv)
+        const double fe = wr0 * (1.0 + (-k15) * p.gammainv);
+        neg |= (fe < 0.0);
+        if (METHOD == 1) f[0] = f[0] - p.omega * (f[0] - fe);        // 3D:286
+        else             f[0] = p.omomega * f[0] + p.omega * fe;     // 3D:246
+    }
+#define LBM_PAIR(q, c, cc, wr)                                                                       \
+    {                                                                                                \
+        const double t3 = 3.0 * (c);                                                                 \
+        const double E = (4.5 * (cc) - k15) * p.gammainv;                                            \
+        const double fe1 = (wr) * ((1.0 + t3) + E);                                                  \
+        const double fe2 = (wr) * ((1.0 - t3) + E);                                                  \
+        neg |= (fe1 < 0.0) | (fe2 < 0.0);                                                            \
+        if (METHOD == 1) { /* 3D:293-302 */                                                          \
+            double fplus = 0.5 * (f[q] + f[q + 1]);                                                  \
+            double fminus = 0.5 * (f[q] - f[q + 1]);                                                 \
+            const double feqplus = 0.5 * (fe1 + fe2);                                                \
+            const double feqminus = 0.5 * (fe1 - fe2);                                               \
+            fplus = p.omega * (fplus - feqplus);                                                     \
+            fminus = p.omegam * (fminus - feqminus);                                                 \
+            const double a = f[q] - fplus - fminus;                                                  \
+            const double b = f[q + 1] - fplus + fminus;                                              \
+            f[q] = a;                                                                                \
+            f[q + 1] = b;                                                                            \
+        } else { /* 3D:246 */                                                                        \
+            f[q] = p.omomega * f[q] + p.omega * fe1;                                                 \
+            f[q + 1] = p.omomega * f[q + 1] + p.omega * fe2;                                         \
+        }                                                                                            \
+    }
+    LBM_PAIR(1, u, uu, wr1)
+    LBM_PAIR(3, v, vv, wr1)
+    LBM_PAIR(5, w, ww, wr1)
+    { const double c = u + v; LBM_PAIR(7, c, c * c, wr2) }
+    { const double c = u + w; LBM_PAIR(9, c, c * c, wr2) }
+    { const double c = v + w; LBM_PAIR(11, c, c * c, wr2) }
+    { const double c = u - v; LBM_PAIR(13, c, c * c, wr2) }
+    { const double c = u - w; LBM_PAIR(15, c, c * c, wr2) }
+    { const double c = v - w; LBM_PAIR(17, c, c * c, wr2) }
+#undef LBM_PAIR
+    return neg;
+}
+
+// ---- wall / lid / edge / corner rules (HechtBC, 3D:385-675) --------------------------------------
+#define LBM_OPP(q) (((q) & 1) ? (q) + 1 : (q) - 1)
+#define LBM_EDGE_OP_Z(x) (x)
+#define LBM_EDGE_OP_P(x) ((x) + temp)
+#define LBM_EDGE_OP_M(x) ((x) - temp)
+
+#define LBM_FACE_CASE(bx, by, bz, un, on, a0, a1, a2, b0, b1, b2, c0, c1, c2, d0, d1, d2, u0, o0, s0, u1, o1, \
+                      s1, u2, o2, s2, u3, o3, s3)                                                             \
+    case LBM_CLS(bx, by, bz): {                                                                               \
+        f[un] = f[on];                                                                                        \
+        const double n0 = 0.5 * ((f[a0] + f[a1] + f[a2]) - (f[b0] + f[b1] + f[b2]));                          \
+        const double n1 = 0.5 * ((f[c0] + f[c1] + f[c2]) - (f[d0] + f[d1] + f[d2]));                          \
+        f[u0] = f[o0] s0 n0;                                                                                  \
+        f[u1] = f[o1] s1 n0;                                                                                  \
+        f[u2] = f[o2] s2 n1;                                                                                  \
+        f[u3] = f[o3] s3 n1;                                                                                  \
+    } break;
+
+#define LBM_EDGE_CASE(bx, by, bz, coef, ta, tb, u0, s0, u1, s1, u2, s2, u3, s3, u4, s4, u5, s5, u6, s6, u7, s7, \
+                      u8, s8)                                                                                   \
+    case LBM_CLS(bx, by, bz): {                                                                                 \
+        const double temp = (coef) * (f[ta] - f[tb]);                                                           \
+        f[u0] = LBM_EDGE_OP_##s0(f[LBM_OPP(u0)]);                                                               \
+        f[u1] = LBM_EDGE_OP_##s1(f[LBM_OPP(u1)]);                                                               \
+        f[u2] = LBM_EDGE_OP_##s2(f[LBM_OPP(u2)]);                                                               \
+        f[u3] = LBM_EDGE_OP_##s3(f[LBM_OPP(u3)]);                                                               \
+        f[u4] = LBM_EDGE_OP_##s4(f[LBM_OPP(u4)]);                                                               \
+        f[u5] = LBM_EDGE_OP_##s5(f[LBM_OPP(u5)]);                                                               \
+        f[u6] = LBM_EDGE_OP_##s6(f[LBM_OPP(u6)]);                                                               \
+        f[u7] = LBM_EDGE_OP_##s7(f[LBM_OPP(u7)]);                                                               \
+        f[u8] = LBM_EDGE_OP_##s8(f[LBM_OPP(u8)]);                                                               \
+    } break;
+
+#define LBM_CORNER_CASE(bx, by, bz, u0, u1, u2, u3, u4, u5) \
+    case LBM_CLS(bx, by, bz): {                             \
+        f[u0] = f[LBM_OPP(u0)];                             \
+        f[u1] = f[LBM_OPP(u1)];                             \
+        f[u2] = f[LBM_OPP(u2)];                             \
+        f[u3] = f[LBM_OPP(u3)];                             \
+        f[u4] = f[LBM_OPP(u4)];                             \
+        f[u5] = f[LBM_OPP(u5)];                             \
+    } break;
+
+__device__ __forceinline__ void apply_boundary(double (&f)[Q], const int cls, const KP &p) {
+    switch (cls) {
+        LBM_D3Q19_FACES(LBM_FACE_CASE)
+        case LBM_CLS(0, 2, 0): {  // the moving lid y = N-1, 3D:437-445
+            const double rho =
+                p.vfrac * (f[1] + f[2] + f[5] + f[6] + f[9] + f[15] + f[16] + f[10] + f[0] +
+                           2.0 * (f[3] + f[7] + f[14] + f[11] + f[17]));
+            f[4] = f[3] - rho * p.vlid * p.third;
+            const double nyx = 0.5 * ((f[1] + f[9] + f[15]) - (f[2] + f[16] + f[10])) - rho * p.ulid * p.third;
+            const double nyz = 0.5 * ((f[5] + f[9] + f[16]) - (f[6] + f[15] + f[10])) - rho * p.wlid * p.third;
+            f[8] = f[7] - rho * (p.vlid + p.ulid) * p.sixth + nyx;
+            f[13] = f[14] + rho * (-p.vlid + p.ulid) * p.sixth - nyx;
+            f[12] = f[11] - rho * (p.vlid + p.wlid) * p.sixth + nyz;
+            f[18] = f[17] + rho * (-p.vlid + p.wlid) * p.sixth - nyz;
+        } break;
+        LBM_D3Q19_EDGES(LBM_EDGE_CASE)
+        LBM_D3Q19_CORNERS(LBM_CORNER_CASE)
+        default: break;
+    }
+}
+
+// ---- block reduction (deterministic: fixed shuffle tree, fixed warp order) -------------------------
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double warp_part[32];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int nthreads = blockDim.x * blockDim.y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) warp_part[tid >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (tid == 0) {
+        const int nw = (nthreads + 31) >> 5;
+        for (int w = 0; w < nw; w++) s += warp_part[w];
+    }
+    return s;  // valid in thread 0
+}
+
+// ---- the fused step kernel ------------------------------------------------------------------------
+// grid = (ceil(N/bx), ceil(N/by), planes of this launch); block = (bx, by), bx*by <= 256.
+template <int METHOD, int MODE>
+__global__ void __launch_bounds__(256, 2) k_step(const __grid_constant__ KP p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int kl = p.kl0 + blockIdx.z * p.kstride;
+    const bool active = (i < p.N) && (j < p.N);
+    double dsum = 0.0;
+
+    if (active) {
+        const int kg = kl + p.k0;
+        const int bx = (i == 0) ? 1 : ((i == p.M) ? 2 : 0);
+        const int by = (j == 0) ? 1 : ((j == p.M) ? 2 : 0);
+        const int bz = (kg == 0) ? 1 : ((kg == p.Mz) ? 2 : 0);
+        const int cls = LBM_CLS(bx, by, bz);
+        const long long N1 = p.N, N2 = p.N2, PS = p.PS;
+        const long long rowcell = (long long)j * N1 + i;
+        const double *s = p.src + ((long long)(kl + 1) * N2 + rowcell);
+
+        double f[Q];
+        // 1. pull.  Source x - c_q; outside the box the reference never writes the slot, which
+        //    therefore still holds w[q] (buried slots) or is overwritten by the rule below.
+#define LBM_PULL(q, cx, cy, cz, wq)                                                                  \
+        {                                                                                            \
+            const bool in = !((cx == 1 && bx == 1) || (cx == -1 && bx == 2) || (cy == 1 && by == 1) || \
+                              (cy == -1 && by == 2) || (cz == 1 && bz == 1) || (cz == -1 && bz == 2)); \
+            f[q] = in ? s[(long long)(q) * PS - ((long long)(cx) + (long long)(cy) * N1 + (long long)(cz) * N2)] \
+                      : (wq);                                                                        \
+        }
+        LBM_D3Q19_VEL(LBM_PULL)
+#undef LBM_PULL
+
+        // 2. boundary rule of this cell's class
+        if (cls != 0) {
+            const bool xm_face = (cls == LBM_CLS(2, 0, 0));
+            // stale f14 (3D:421): at x = N-1 the rule reads population 14 before assigning it; the
+            // reference finds there what HechtBC wrote into the same buffer two iterations ago.
+            if (xm_face) f[14] = p.side_rd[(long long)kl * N1 + j];
+            apply_boundary(f, cls, p);
+            if (MODE != MODE_MATERIALISE) {
+                if (xm_face) p.side_wr[(long long)kl * N1 + j] = f[14];
+            }
+        }
+
+        // f == the reference's f2[x][:] after HechtBC of this iteration
+        if (MODE != MODE_STEP) {
+            double *F = p.Fbuf + ((long long)kl * N2 + rowcell);
+            if (MODE == MODE_STEP_DIFF_STOREF) {
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    const double d = f[q] - F[(long long)q * p.FS];
+                    dsum += d * d;   // diff(), 3D:682 (the reference's summation order is unspecified)
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < Q; q++) F[(long long)q * p.FS] = f[q];
+        }
+
+        // 3. collide + store
+        if (MODE != MODE_MATERIALISE) {
+            const bool neg = collide<METHOD>(f, p);
+            if (neg) atomicOr(p.flag, 1);
+            double *d = p.dst + ((long long)(kl + 1) * N2 + rowcell);
+#pragma unroll
+            for (int q = 0; q < Q; q++) d[(long long)q * PS] = f[q];
+        }
+    }
+
+    if (MODE == MODE_STEP_DIFF_STOREF) {
+        const double s = block_sum(dsum);
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            const long long bid = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            p.partials[p.partial_base + bid] = s;
+        }
+    }
+}
+
+// S = collide(F) for every owned cell, F taken from the F buffer (restart, lbm_set_f), or
+// F = w (initial state, 3D:192-205: feq(rho=1,u=0) = w[q] exactly) when Fbuf == nullptr.
+// Covers ghost planes too when `with_ghosts` (initial state only: uniform).
+template <int METHOD>
+__global__ void __launch_bounds__(256, 2) k_collide_cells(const __grid_constant__ KP p, const int with_ghosts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int kl = (int)blockIdx.z - (with_ghosts ? 1 : 0);
+    if (i >= p.N || j >= p.N) return;
+    const long long rowcell = (long long)j * p.N + i;
+    double f[Q];
+    if (p.Fbuf != nullptr && !with_ghosts) {
+        const double *F = p.Fbuf + ((long long)kl * p.N2 + rowcell);
+#pragma unroll
+        for (int q = 0; q < Q; q++) f[q] = F[(long long)q * p.FS];
+    } else {
+#define LBM_SETW(q, cx, cy, cz, wq) f[q] = (wq);
+        LBM_D3Q19_VEL(LBM_SETW)
+#undef LBM_SETW
+    }
+    const bool neg = collide<METHOD>(f, p);
+    if (neg) atomicOr(p.flag, 1);
+    double *d = p.dst + ((long long)(kl + 1) * p.N2 + rowcell);
+#pragma unroll
+    for (int q = 0; q < Q; q++) d[(long long)q * p.PS] = f[q];
+}
+
+// Fill the F buffer with the initial distributions f = w[q] (3D:192-205).
+__global__ void k_fill_w(double *F, long long FS) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= FS) return;
+#define LBM_FILLW(q, cx, cy, cz, wq) F[(long long)(q) * FS + n] = (wq);
+    LBM_D3Q19_VEL(LBM_FILLW)
+#undef LBM_FILLW
+}
+
+__global__ void k_fill(double *a, long long n, double v) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) a[t] = v;
+}
+
+// macrovars (3D:695-719) + calcvmag (3D:730-738) from the F buffer.
+__global__ void __launch_bounds__(256) k_macrovars(const double *__restrict__ F, long long FS, double *u1,
+                                                   double *u2, double *u3, double *rho, double *vmag) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= FS) return;
+    double f[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) f[q] = F[(long long)q * FS + n];
+    // `+=` loops over q = 0..18 starting from 0.0 (3D:701-711); zero terms are exact
+    double r = 0.0 + f[0];
+#pragma unroll
+    for (int q = 1; q < Q; q++) r += f[q];
+    double us = 0.0 + f[1];
+    us -= f[2]; us += f[7]; us -= f[8]; us += f[9]; us -= f[10]; us += f[13]; us -= f[14]; us += f[15]; us -= f[16];
+    double vs = 0.0 + f[3];
+    vs -= f[4]; vs += f[7]; vs -= f[8]; vs += f[11]; vs -= f[12]; vs -= f[13]; vs += f[14]; vs += f[17]; vs -= f[18];
+    double ws = 0.0 + f[5];
+    ws -= f[6]; ws += f[9]; ws -= f[10]; ws += f[11]; ws -= f[12]; ws -= f[15]; ws += f[16]; ws -= f[17]; ws += f[18];
+    const double u = us / r, v = vs / r, w = ws / r;   // 3D:713-715 divides
+    if (rho) rho[n] = r;
+    if (u1) u1[n] = u;
+    if (u2) u2[n] = v;
+    if (u3) u3[n] = w;
+    if (vmag) vmag[n] = sqrt((u * u + v * v) + w * w);  // 3D:735
+}
+
+// Second stage of the residual: one block sums the block partials in a fixed order.
+__global__ void __launch_bounds__(1024) k_sum_partials(const double *__restrict__ part, long long n, double *out) {
+    __shared__ double sm[1024];
+    double s = 0.0;
+    for (long long t = threadIdx.x; t < n; t += 1024) s += part[t];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sm[0];
+}
+
+}  // namespace lbm3d

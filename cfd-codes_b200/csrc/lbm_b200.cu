@@ -1,0 +1,690 @@
+// lbm_b200.cu -- host side of the C ABI declared in include/lbm_b200.h (contexts, streams, slabs,
+// NCCL halo exchange) for the D3Q19 cavity path.  See DESIGN.md for the state machine.
+//
+// Reference being replaced: /root/reference/3D Lid-driven Cavity with Lattice Boltzmann Method/main.c
+// ("3D:"): allocate/initialize 3D:135-206, the time loop 3D:94-124, diff 3D:678, macrovars 3D:695.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/lbm_b200.h"
+#include "lbm3d_kernels.cuh"
+
+// ---- error plumbing ------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(e_ == cudaErrorMemoryAllocation ? LBM_ERR_NOMEM : LBM_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                 \
+    } while (0)
+
+// ---- NCCL through dlopen (only touched when nranks > 1) ---------------------------------------
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    const char *(*GetErrorString)(ncclResult_t);
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.h) return LBM_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    void *h = nullptr;
+    for (int i = 0; names[i] && !h; i++) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(LBM_ERR_NCCL, "dlopen(libnccl.so.2) failed: %s", dlerror());
+#define SYM(field, name)                                                         \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                                  \
+    if (!g_nccl.field) return fail(LBM_ERR_NCCL, "dlsym(%s) failed", name);
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
+    SYM(AllReduce, "ncclAllReduce")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.h = h;
+    return LBM_OK;
+}
+
+#define NK(call)                                                                                      \
+    do {                                                                                              \
+        ncclResult_t r_ = (call);                                                                     \
+        if (r_ != ncclSuccess)                                                                        \
+            return fail(LBM_ERR_NCCL, "%s: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
+// populations that cross a z face (velocities 3D:36-38): cz = +1 and cz = -1
+static const int Q_UP[5] = {5, 9, 11, 16, 18};
+static const int Q_DN[5] = {6, 10, 12, 15, 17};
+
+// ---- context -----------------------------------------------------------------------------------
+struct lbm_ctx {
+    lbm_params prm;
+    int dev = 0;
+    cudaStream_t s_main = nullptr, s_halo = nullptr;
+    bool own_main = false;
+    cudaEvent_t ev_bnd = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    bool halo_pending = false;  // ev_halo has been recorded and not yet waited on by s_main
+
+    int N = 0, nzl = 0, k0 = 0, k1 = 0;
+    long long N2 = 0, PS = 0, FS = 0;
+    double NU, TAU, OMEGA, OMEGAm, OmOMEGA, gammainv, ulid, vlid, wlid;
+
+    double *lat[2] = {nullptr, nullptr};  // post-collision lattices, ghost plane first
+    int cur = 0;                          // lat[cur] holds S of the latest iteration
+    double *Fbuf = nullptr;               // the reference's f2 of the latest iteration when f_valid
+    bool f_valid = false;
+    double *side = nullptr;               // [3][nzl][N] stale-f14 history of the x = N-1 face
+    double *partials = nullptr;
+    long long npartials = 0;
+    double *d_red = nullptr;  // [0] local sum, [1] all-reduced sum
+    int *d_flag = nullptr;
+    double *d_out[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // macrovars staging
+    double *h_pin = nullptr;                                         // pinned: [0..1] sums, [2] flag (as double slot)
+    bool residual_ready = false;
+    bool unstable = false;
+
+    long long steps = 0, launches = 0, bytes = 0;
+    int block_x = 0, block_y = 0;
+    bool host_local = false;  // host arrays are compact local slabs instead of full LU4/LU3 arrays
+    ncclComm_t comm = nullptr;
+};
+
+template <typename T>
+static int dev_alloc(lbm_ctx *c, T **p, long long count) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (size_t)count * sizeof(T));
+    if (e != cudaSuccess)
+        return fail(LBM_ERR_NOMEM, "cudaMalloc(%lld bytes): %s", count * (long long)sizeof(T), cudaGetErrorString(e));
+    c->bytes += count * (long long)sizeof(T);
+    *p = (T *)q;
+    return LBM_OK;
+}
+
+static void choose_block(const lbm_ctx *c, dim3 *blk, dim3 *grd_xy) {
+    int bx = c->block_x, by = c->block_y;
+    if (bx <= 0) {
+        bx = ((c->N + 31) / 32) * 32;
+        if (bx > 256) bx = 256;
+        // prefer a divisor of the row so that no lanes idle (N = 512 -> 256, N = 320 -> 160)
+        if (c->N > 256) {
+            for (int cand = 256; cand >= 64; cand -= 32)
+                if (c->N % cand == 0) { bx = cand; break; }
+        }
+    }
+    if (by <= 0) {
+        by = 256 / bx;
+        if (by < 1) by = 1;
+        if (by > c->N) by = c->N;
+    }
+    *blk = dim3(bx, by, 1);
+    *grd_xy = dim3((c->N + bx - 1) / bx, (c->N + by - 1) / by, 1);
+}
+
+static lbm3d::KP make_kp(const lbm_ctx *c) {
+    lbm3d::KP p;
+    memset(&p, 0, sizeof(p));
+    p.N = c->N; p.M = c->N - 1; p.Mz = c->N - 1;
+    p.nzl = c->nzl; p.k0 = c->k0;
+    p.kl0 = 0; p.kstride = 1; p.partial_base = 0;
+    p.N2 = c->N2; p.PS = c->PS; p.FS = c->FS;
+    p.omega = c->OMEGA; p.omegam = c->OMEGAm; p.omomega = c->OmOMEGA; p.gammainv = c->gammainv;
+    p.ulid = c->ulid; p.vlid = c->vlid; p.wlid = c->wlid;
+    p.vfrac = 1.0 / (c->vlid + 1.0);  // 3D:386
+    p.third = 1.0 / 3.0;              // 3D:42
+    p.sixth = 1.0 / 6.0;              // 3D:41
+    p.flag = c->d_flag;
+    p.partials = c->partials;
+    p.Fbuf = c->Fbuf;
+    return p;
+}
+
+template <int MODE>
+static void launch_step_mode(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, dim3 blk) {
+    if (c->prm.METHOD == 1) lbm3d::k_step<1, MODE><<<grid, blk, 0, c->s_main>>>(p);
+    else                    lbm3d::k_step<0, MODE><<<grid, blk, 0, c->s_main>>>(p);
+    c->launches++;
+}
+
+static void launch_step(lbm_ctx *c, int mode, const lbm3d::KP &p, dim3 grid, dim3 blk) {
+    switch (mode) {
+        case lbm3d::MODE_STEP: launch_step_mode<lbm3d::MODE_STEP>(c, p, grid, blk); break;
+        case lbm3d::MODE_STEP_STOREF: launch_step_mode<lbm3d::MODE_STEP_STOREF>(c, p, grid, blk); break;
+        case lbm3d::MODE_STEP_DIFF_STOREF: launch_step_mode<lbm3d::MODE_STEP_DIFF_STOREF>(c, p, grid, blk); break;
+        default: launch_step_mode<lbm3d::MODE_MATERIALISE>(c, p, grid, blk); break;
+    }
+}
+
+static long long blocks_per_plane(const lbm_ctx *c) {
+    dim3 blk, g;
+    choose_block(c, &blk, &g);
+    return (long long)g.x * g.y;
+}
+
+static int ensure_Fbuf(lbm_ctx *c) {
+    if (c->Fbuf) return LBM_OK;
+    int rc = dev_alloc(c, &c->Fbuf, (long long)lbm3d::Q * c->FS);
+    if (rc) return rc;
+    c->f_valid = false;
+    return LBM_OK;
+}
+
+static int ensure_partials(lbm_ctx *c) {
+    const long long need = blocks_per_plane(c) * c->nzl;
+    if (c->partials && c->npartials >= need) return LBM_OK;
+    if (c->partials) { cudaFree(c->partials); c->bytes -= c->npartials * 8; c->partials = nullptr; }
+    int rc = dev_alloc(c, &c->partials, need);
+    if (rc) return rc;
+    c->npartials = need;
+    return LBM_OK;
+}
+
+// Exchange the face-crossing populations of lattice `L` (just written) with the z-neighbours.
+// Up-going populations (cz=+1) of my top plane -> bottom ghost of rank+1; down-going (cz=-1) of my
+// bottom plane -> top ghost of rank-1.  Each is one contiguous N^2 block (z is the slowest axis, 3D:48).
+static int halo_exchange(lbm_ctx *c, double *L, cudaStream_t st) {
+    const int r = c->prm.rank, P = c->prm.nranks;
+    const size_t n = (size_t)c->N2;
+    NK(g_nccl.GroupStart());
+    for (int a = 0; a < 5; a++) {
+        if (r + 1 < P) {
+            NK(g_nccl.Send(L + (long long)Q_UP[a] * c->PS + (long long)c->nzl * c->N2, n, ncclDouble, r + 1, c->comm, st));
+            NK(g_nccl.Recv(L + (long long)Q_DN[a] * c->PS + (long long)(c->nzl + 1) * c->N2, n, ncclDouble, r + 1, c->comm, st));
+        }
+        if (r > 0) {
+            NK(g_nccl.Send(L + (long long)Q_DN[a] * c->PS + (long long)1 * c->N2, n, ncclDouble, r - 1, c->comm, st));
+            NK(g_nccl.Recv(L + (long long)Q_UP[a] * c->PS + (long long)0 * c->N2, n, ncclDouble, r - 1, c->comm, st));
+        }
+    }
+    NK(g_nccl.GroupEnd());
+    return LBM_OK;
+}
+
+// One iteration in the given mode.  Reads lat[cur], writes lat[cur^1] (unless MATERIALISE).
+static int run_iteration(lbm_ctx *c, int mode) {
+    dim3 blk, gxy;
+    choose_block(c, &blk, &gxy);
+    lbm3d::KP p = make_kp(c);
+    const bool real = (mode != lbm3d::MODE_MATERIALISE);
+    // iteration index t = c->steps (real step) or c->steps - 1 (re-materialising the last one)
+    const long long t = real ? c->steps : c->steps - 1;
+    const int src_i = real ? c->cur : (c->cur ^ 1);
+    p.src = c->lat[src_i];
+    p.dst = c->lat[src_i ^ 1];
+    const long long side_n = (long long)c->nzl * c->N;
+    p.side_rd = c->side + ((t + 1) % 3) * side_n;  // written by iteration t-2
+    p.side_wr = c->side + (t % 3) * side_n;
+    const long long bpp = (long long)gxy.x * gxy.y;
+
+    const bool multi = c->prm.nranks > 1;
+    if (!multi || !real) {
+        if (multi && c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
+        p.kl0 = 0; p.kstride = 1; p.partial_base = 0;
+        launch_step(c, mode, p, dim3(gxy.x, gxy.y, c->nzl), blk);
+    } else {
+        // boundary planes first (they need the ghosts received after the previous iteration and
+        // feed this iteration's exchange), then the interior overlaps the NCCL transfer.
+        if (c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
+        const int nb = c->nzl >= 2 ? 2 : 1;
+        p.kl0 = 0; p.kstride = c->nzl >= 2 ? c->nzl - 1 : 1; p.partial_base = 0;
+        launch_step(c, mode, p, dim3(gxy.x, gxy.y, nb), blk);
+        CK(cudaEventRecord(c->ev_bnd, c->s_main));
+        CK(cudaStreamWaitEvent(c->s_halo, c->ev_bnd, 0));
+        int rc = halo_exchange(c, c->lat[src_i ^ 1], c->s_halo);
+        if (rc) return rc;
+        CK(cudaEventRecord(c->ev_halo, c->s_halo));
+        c->halo_pending = true;
+        if (c->nzl > 2) {
+            p.kl0 = 1; p.kstride = 1; p.partial_base = (int)(bpp * nb);
+            launch_step(c, mode, p, dim3(gxy.x, gxy.y, c->nzl - 2), blk);
+        }
+    }
+    CK(cudaGetLastError());
+    if (real) {
+        c->cur ^= 1;
+        c->steps++;
+        c->f_valid = (mode != lbm3d::MODE_STEP);
+        c->residual_ready = false;
+        if (mode == lbm3d::MODE_STEP_DIFF_STOREF) {
+            lbm3d::k_sum_partials<<<1, 1024, 0, c->s_main>>>(c->partials, bpp * c->nzl, c->d_red);
+            c->launches++;
+            CK(cudaGetLastError());
+            c->residual_ready = true;
+        }
+    } else {
+        c->f_valid = true;
+    }
+    return LBM_OK;
+}
+
+// Make Fbuf hold the reference's f2 of the latest iteration.
+static int materialise_F(lbm_ctx *c) {
+    int rc = ensure_Fbuf(c);
+    if (rc) return rc;
+    if (c->f_valid) return LBM_OK;
+    if (c->steps == 0) {
+        const long long n = c->FS;
+        lbm3d::k_fill_w<<<(unsigned)((n + 255) / 256), 256, 0, c->s_main>>>(c->Fbuf, c->FS);
+        c->launches++;
+        CK(cudaGetLastError());
+        c->f_valid = true;
+        return LBM_OK;
+    }
+    return run_iteration(c, lbm3d::MODE_MATERIALISE);
+}
+
+static int poll_flag(lbm_ctx *c) {
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->s_main));
+    CK(cudaStreamSynchronize(c->s_main));
+    if (c->s_halo) CK(cudaStreamSynchronize(c->s_halo));
+    if (flag) c->unstable = true;
+    if (c->unstable) return fail(LBM_ERR_UNSTABLE, "Error: negative feq.  Therefore, unstable.");
+    return LBM_OK;
+}
+
+// ---- C ABI ---------------------------------------------------------------------------------------
+extern "C" {
+
+const char *lbm_last_error(void) { return g_err; }
+
+const char *lbm_version(void) { return "lbm_b200 0.1 (sm_100a, fp64, -fmad=false, D3Q19 pull/two-lattice)"; }
+
+void lbm_default_params(lbm_params *p) {
+    memset(p, 0, sizeof(*p));
+    p->dim = 3; p->N = 50; p->M = 0; p->Re = 100; p->UMAX = 0.1;   // 3D:7-9
+    p->METHOD = 1; p->GAMMA = 1.0; p->MAGIC = 0.25; p->DIAG = 0;   // 3D:12-14, 22
+    p->rank = 0; p->nranks = 1; p->device = -1; p->track_residual = 1; p->stream = nullptr;
+}
+
+int lbm_nccl_unique_id(unsigned char out[LBM_NCCL_ID_BYTES]) {
+    int rc = nccl_load();
+    if (rc) return rc;
+    ncclUniqueId id;
+    NK(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(id) == LBM_NCCL_ID_BYTES, "ncclUniqueId size");
+    memcpy(out, &id, LBM_NCCL_ID_BYTES);
+    return LBM_OK;
+}
+
+int lbm_destroy(lbm_ctx *c) {
+    if (!c) return LBM_OK;
+    cudaSetDevice(c->dev);
+    if (c->s_main) cudaStreamSynchronize(c->s_main);
+    if (c->s_halo) cudaStreamSynchronize(c->s_halo);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    cudaFree(c->lat[0]); cudaFree(c->lat[1]); cudaFree(c->Fbuf); cudaFree(c->side);
+    cudaFree(c->partials); cudaFree(c->d_red); cudaFree(c->d_flag);
+    for (int a = 0; a < 5; a++) cudaFree(c->d_out[a]);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
+    if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    if (c->s_halo) cudaStreamDestroy(c->s_halo);
+    if (c->own_main && c->s_main) cudaStreamDestroy(c->s_main);
+    delete c;
+    return LBM_OK;
+}
+
+static int create3d(lbm_ctx *c) {
+    const lbm_params &p = c->prm;
+    c->N = p.N;
+    c->N2 = (long long)p.N * p.N;
+    c->k0 = (int)((long long)p.rank * p.N / p.nranks);
+    c->k1 = (int)((long long)(p.rank + 1) * p.N / p.nranks);
+    c->nzl = c->k1 - c->k0;
+    if (c->nzl < 1) return fail(LBM_ERR_INVALID, "rank %d of %d owns no plane of N=%d", p.rank, p.nranks, p.N);
+    c->PS = (long long)(c->nzl + 2) * c->N2;
+    c->FS = (long long)c->nzl * c->N2;
+    if (c->FS >= (1LL << 31)) return fail(LBM_ERR_INVALID, "more than 2^31 cells per GPU");
+
+    // derived constants in the reference's macro order (3D:19-23, 30, 40) so the doubles are
+    // bit-identical to gcc's constant folding
+    const int Re = (int)p.Re;
+    c->NU = (p.UMAX) * (double)(p.N + 1.0) / (double)(Re);
+    c->TAU = (c->NU) * (3.0 / (double)p.GAMMA) + 0.5;
+    c->OMEGA = 1.0 / (double)(c->TAU);
+    c->OMEGAm = 1.0 / (0.5 + (p.MAGIC / ((1.0 / c->OMEGA) - 0.5)));
+    c->OmOMEGA = 1.0 - c->OMEGA;
+    c->gammainv = 1.0 / p.GAMMA;
+    if (p.DIAG == 1) {  // 3D:183-191
+        c->ulid = (double)p.UMAX / sqrt(2.0);
+        c->wlid = c->ulid;
+    } else {
+        c->ulid = p.UMAX;
+        c->wlid = 0.0;
+    }
+    c->vlid = 0.0;
+
+    int rc;
+    if ((rc = dev_alloc(c, &c->lat[0], (long long)lbm3d::Q * c->PS))) return rc;
+    if ((rc = dev_alloc(c, &c->lat[1], (long long)lbm3d::Q * c->PS))) return rc;
+    const long long side_n = (long long)c->nzl * c->N;
+    if ((rc = dev_alloc(c, &c->side, 3 * side_n))) return rc;
+    if ((rc = dev_alloc(c, &c->d_red, 2))) return rc;
+    if ((rc = dev_alloc(c, &c->d_flag, 1))) return rc;
+    CK(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->s_main));
+    CK(cudaMemsetAsync(c->d_red, 0, 2 * sizeof(double), c->s_main));
+    CK(cudaMallocHost((void **)&c->h_pin, 4 * sizeof(double)));
+
+    // stale-f14 history starts at the initial value w[14] = 1/36 (3D:192-205)
+    lbm3d::k_fill<<<(unsigned)((3 * side_n + 255) / 256), 256, 0, c->s_main>>>(c->side, 3 * side_n, LBM_W2);
+    c->launches++;
+
+    // S(-1) = collide(f = w) in both lattices incl. ghost planes (colliding the initial equilibrium
+    // is NOT a no-op in fp64: sum of w[q] != 1)
+    dim3 blk, gxy;
+    choose_block(c, &blk, &gxy);
+    for (int l = 0; l < 2; l++) {
+        lbm3d::KP kp = make_kp(c);
+        kp.dst = c->lat[l];
+        kp.Fbuf = nullptr;
+        dim3 grid(gxy.x, gxy.y, c->nzl + 2);
+        if (p.METHOD == 1) lbm3d::k_collide_cells<1><<<grid, blk, 0, c->s_main>>>(kp, 1);
+        else               lbm3d::k_collide_cells<0><<<grid, blk, 0, c->s_main>>>(kp, 1);
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+    c->cur = 0;
+    c->steps = 0;
+    if (p.track_residual) {
+        if ((rc = materialise_F(c))) return rc;  // Fbuf = w: the reference's f1 before iteration 0 (3D:96)
+        if ((rc = ensure_partials(c))) return rc;
+    }
+    CK(cudaStreamSynchronize(c->s_main));
+    return LBM_OK;
+}
+
+int lbm_create(const lbm_params *p, lbm_ctx **out) {
+    if (!p || !out) return fail(LBM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (p->dim != 3) return fail(LBM_ERR_INVALID, "dim=%d not supported by this build (3 = D3Q19)", p->dim);
+    if (p->N < 3) return fail(LBM_ERR_INVALID, "N=%d: need at least 3 grid points per side", p->N);
+    if (p->METHOD != 0 && p->METHOD != 1) return fail(LBM_ERR_INVALID, "METHOD=%d (0 = BGK, 1 = TRT)", p->METHOD);
+    if (!(p->Re > 0) || p->Re != floor(p->Re)) return fail(LBM_ERR_INVALID, "Re must be a positive integer (3D:7)");
+    if (!(p->GAMMA > 0)) return fail(LBM_ERR_INVALID, "GAMMA must be positive");
+    if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks) return fail(LBM_ERR_INVALID, "bad rank/nranks");
+    if (p->nranks > p->N) return fail(LBM_ERR_INVALID, "more ranks than z planes");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(LBM_ERR_CUDA, "no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    lbm_ctx *c = new lbm_ctx();
+    c->prm = *p;
+    if (p->device >= 0) {
+        if (p->device >= ndev) { delete c; return fail(LBM_ERR_INVALID, "device %d of %d", p->device, ndev); }
+        c->dev = p->device;
+    } else {
+        cudaGetDevice(&c->dev);
+    }
+    int rc = LBM_OK;
+#define CKD(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            rc = fail(LBM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));                              \
+            lbm_destroy(c);                                                                                \
+            return rc;                                                                                     \
+        }                                                                                                  \
+    } while (0)
+    CKD(cudaSetDevice(c->dev));
+    if (p->stream) {
+        c->s_main = (cudaStream_t)p->stream;
+    } else {
+        CKD(cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking));
+        c->own_main = true;
+    }
+    CKD(cudaEventCreate(&c->ev_t0));
+    CKD(cudaEventCreate(&c->ev_t1));
+    if (p->nranks > 1) {
+        int lo, hi;
+        CKD(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CKD(cudaStreamCreateWithPriority(&c->s_halo, cudaStreamNonBlocking, hi));
+        CKD(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
+        CKD(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+        if ((rc = nccl_load())) { lbm_destroy(c); return rc; }
+        ncclUniqueId id;
+        memcpy(&id, p->nccl_id, LBM_NCCL_ID_BYTES);
+        ncclResult_t r = g_nccl.CommInitRank(&c->comm, p->nranks, id, p->rank);
+        if (r != ncclSuccess) {
+            rc = fail(LBM_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+            c->comm = nullptr;
+            lbm_destroy(c);
+            return rc;
+        }
+    }
+#undef CKD
+    rc = create3d(c);
+    if (rc) { lbm_destroy(c); return rc; }
+    *out = c;
+    return LBM_OK;
+}
+
+int lbm_step(lbm_ctx *c, long long n) {
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    if (n < 0) return fail(LBM_ERR_INVALID, "negative step count");
+    if (c->unstable) return fail(LBM_ERR_UNSTABLE, "Error: negative feq.  Therefore, unstable.");
+    CK(cudaSetDevice(c->dev));
+    const bool track = c->prm.track_residual != 0;
+    int rc;
+    if (track && n > 0) {
+        if ((rc = ensure_Fbuf(c))) return rc;
+        if ((rc = ensure_partials(c))) return rc;
+        if (n == 1 && !c->f_valid) { if ((rc = materialise_F(c))) return rc; }
+    }
+    for (long long t = 0; t < n; t++) {
+        int mode = lbm3d::MODE_STEP;
+        if (track) {
+            if (t == n - 1) mode = lbm3d::MODE_STEP_DIFF_STOREF;     // F(t) vs F(t-1): the reference's diff(f2, f1)
+            else if (t == n - 2) mode = lbm3d::MODE_STEP_STOREF;     // leaves F(t-1) for the last iteration
+        }
+        if ((rc = run_iteration(c, mode))) return rc;
+    }
+    return LBM_OK;
+}
+
+int lbm_timer_start(lbm_ctx *c) {
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->dev));
+    CK(cudaStreamSynchronize(c->s_main));
+    if (c->s_halo) CK(cudaStreamSynchronize(c->s_halo));
+    CK(cudaEventRecord(c->ev_t0, c->s_main));
+    return LBM_OK;
+}
+
+int lbm_timer_stop(lbm_ctx *c, float *ms) {
+    if (!c || !ms) return fail(LBM_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->dev));
+    if (c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
+    CK(cudaEventRecord(c->ev_t1, c->s_main));
+    CK(cudaEventSynchronize(c->ev_t1));
+    CK(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+    return LBM_OK;
+}
+
+int lbm_step_timed(lbm_ctx *c, long long n, float *ms) {
+    int rc = lbm_timer_start(c);
+    if (rc) return rc;
+    if ((rc = lbm_step(c, n))) return rc;
+    return lbm_timer_stop(c, ms);
+}
+
+int lbm_residual(lbm_ctx *c, double *out) {
+    if (!c || !out) return fail(LBM_ERR_INVALID, "null argument");
+    if (!c->prm.track_residual) return fail(LBM_ERR_INVALID, "lbm_residual needs track_residual=1");
+    if (!c->residual_ready) return fail(LBM_ERR_INVALID, "lbm_residual: no iteration since creation / lbm_set_f");
+    CK(cudaSetDevice(c->dev));
+    const double *src = c->d_red;
+    if (c->prm.nranks > 1) {
+        NK(g_nccl.AllReduce(c->d_red, c->d_red + 1, 1, ncclDouble, ncclSum, c->comm, c->s_main));
+        src = c->d_red + 1;
+    }
+    CK(cudaMemcpyAsync(c->h_pin, src, sizeof(double), cudaMemcpyDeviceToHost, c->s_main));
+    int rc = poll_flag(c);  // synchronises
+    *out = sqrt(c->h_pin[0]);  // 3D:684
+    return rc;
+}
+
+int lbm_sync(lbm_ctx *c) {
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->dev));
+    return poll_flag(c);
+}
+
+int lbm_get_f(lbm_ctx *c, double *host_full) {
+    if (!c || !host_full) return fail(LBM_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->dev));
+    int rc = materialise_F(c);
+    if (rc) return rc;
+    const long long N3 = c->host_local ? c->FS : c->N2 * c->N;
+    const long long hk0 = c->host_local ? 0 : c->k0;
+    for (int q = 0; q < lbm3d::Q; q++)
+        CK(cudaMemcpyAsync(host_full + (long long)q * N3 + hk0 * c->N2, c->Fbuf + (long long)q * c->FS,
+                           (size_t)c->FS * sizeof(double), cudaMemcpyDeviceToHost, c->s_main));
+    CK(cudaStreamSynchronize(c->s_main));
+    return LBM_OK;
+}
+
+int lbm_set_f(lbm_ctx *c, const double *host_f, const double *host_f_prev) {
+    if (!c || !host_f) return fail(LBM_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->dev));
+    int rc = ensure_Fbuf(c);
+    if (rc) return rc;
+    if (c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
+    const long long N3 = c->host_local ? c->FS : c->N2 * c->N;
+    const long long hk0 = c->host_local ? 0 : c->k0;
+    for (int q = 0; q < lbm3d::Q; q++)
+        CK(cudaMemcpyAsync(c->Fbuf + (long long)q * c->FS, host_f + (long long)q * N3 + hk0 * c->N2,
+                           (size_t)c->FS * sizeof(double), cudaMemcpyHostToDevice, c->s_main));
+    // stale f14 of the x = N-1 face: the next iteration (index `steps`) reads slot (steps+1)%3.
+    // Taken from the reference's other buffer if given, else from the current one.
+    {
+        const double *srcf = host_f_prev ? host_f_prev : host_f;
+        const long long side_n = (long long)c->nzl * c->N;
+        double *tmp = (double *)malloc((size_t)side_n * sizeof(double));
+        if (!tmp) return fail(LBM_ERR_NOMEM, "malloc");
+        for (int kl = 0; kl < c->nzl; kl++)
+            for (int j = 0; j < c->N; j++)
+                tmp[(long long)kl * c->N + j] = srcf[14LL * N3 + (hk0 + kl) * c->N2 + (long long)j * c->N + (c->N - 1)];
+        // slot read by iteration t = steps is (t+1)%3; the one read by t+1 is (t+2)%3 and must be
+        // this state's own post-BC f14, which is in host_f.
+        cudaError_t e = cudaMemcpyAsync(c->side + ((c->steps + 1) % 3) * side_n, tmp, (size_t)side_n * sizeof(double),
+                                        cudaMemcpyHostToDevice, c->s_main);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_main);
+        for (int kl = 0; kl < c->nzl; kl++)
+            for (int j = 0; j < c->N; j++)
+                tmp[(long long)kl * c->N + j] = host_f[14LL * N3 + (hk0 + kl) * c->N2 + (long long)j * c->N + (c->N - 1)];
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(c->side + ((c->steps + 2) % 3) * side_n, tmp, (size_t)side_n * sizeof(double),
+                                cudaMemcpyHostToDevice, c->s_main);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_main);
+        free(tmp);
+        if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "side upload: %s", cudaGetErrorString(e));
+    }
+    // S = collide(F) into lat[cur]
+    dim3 blk, gxy;
+    choose_block(c, &blk, &gxy);
+    lbm3d::KP kp = make_kp(c);
+    kp.dst = c->lat[c->cur];
+    dim3 grid(gxy.x, gxy.y, c->nzl);
+    if (c->prm.METHOD == 1) lbm3d::k_collide_cells<1><<<grid, blk, 0, c->s_main>>>(kp, 0);
+    else                    lbm3d::k_collide_cells<0><<<grid, blk, 0, c->s_main>>>(kp, 0);
+    c->launches++;
+    CK(cudaGetLastError());
+    if (c->prm.nranks > 1) {
+        rc = halo_exchange(c, c->lat[c->cur], c->s_main);
+        if (rc) return rc;
+    }
+    c->f_valid = true;
+    c->residual_ready = false;
+    CK(cudaStreamSynchronize(c->s_main));
+    return LBM_OK;
+}
+
+int lbm_macrovars(lbm_ctx *c, double *u1, double *u2, double *u3, double *rho, double *vmag) {
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->dev));
+    int rc = materialise_F(c);
+    if (rc) return rc;
+    double *host[5] = {u1, u2, u3, rho, vmag};
+    for (int a = 0; a < 5; a++)
+        if (!c->d_out[a]) { if ((rc = dev_alloc(c, &c->d_out[a], c->FS))) return rc; }
+    const long long n = c->FS;
+    lbm3d::k_macrovars<<<(unsigned)((n + 255) / 256), 256, 0, c->s_main>>>(c->Fbuf, c->FS, c->d_out[0], c->d_out[1],
+                                                                          c->d_out[2], c->d_out[3], c->d_out[4]);
+    c->launches++;
+    CK(cudaGetLastError());
+    for (int a = 0; a < 5; a++)
+        if (host[a])
+            CK(cudaMemcpyAsync(host[a] + (c->host_local ? 0LL : (long long)c->k0 * c->N2), c->d_out[a], (size_t)n * sizeof(double),
+                               cudaMemcpyDeviceToHost, c->s_main));
+    CK(cudaStreamSynchronize(c->s_main));
+    return LBM_OK;
+}
+
+int lbm_get_info(lbm_ctx *c, lbm_info *o) {
+    if (!c || !o) return fail(LBM_ERR_INVALID, "null argument");
+    memset(o, 0, sizeof(*o));
+    o->NU = c->NU; o->TAU = c->TAU; o->OMEGA = c->OMEGA; o->OMEGAm = c->OMEGAm; o->OmOMEGA = c->OmOMEGA;
+    o->ulid = c->ulid; o->vlid = c->vlid; o->wlid = c->wlid;
+    o->Q = lbm3d::Q; o->k0 = c->k0; o->k1 = c->k1;
+    o->cells_local = c->FS; o->cells_global = c->N2 * c->N;
+    o->steps_done = c->steps; o->kernel_launches = c->launches; o->device_bytes = c->bytes;
+    return LBM_OK;
+}
+
+int lbm_set_option(lbm_ctx *c, const char *key, long long value) {
+    if (!c || !key) return fail(LBM_ERR_INVALID, "null argument");
+    if (!strcmp(key, "block_x")) {
+        if (value < 0 || value > 256 || (value % 32)) return fail(LBM_ERR_INVALID, "block_x must be a multiple of 32 <= 256");
+        c->block_x = (int)value;
+    } else if (!strcmp(key, "block_y")) {
+        if (value < 0 || value > 256) return fail(LBM_ERR_INVALID, "block_y out of range");
+        c->block_y = (int)value;
+    } else if (!strcmp(key, "host_local_layout")) {
+        c->host_local = value != 0;
+        return LBM_OK;
+    } else if (!strcmp(key, "track_residual")) {
+        c->prm.track_residual = value != 0;
+        c->residual_ready = false;
+        return LBM_OK;
+    } else {
+        return fail(LBM_ERR_INVALID, "unknown option %s", key);
+    }
+    if (c->block_x > 0 && c->block_y > 0 && c->block_x * c->block_y > 256)
+        return fail(LBM_ERR_INVALID, "block_x*block_y > 256");
+    // partial-sum buffer depends on the block shape
+    if (c->prm.track_residual) return ensure_partials(c);
+    return LBM_OK;
+}
+
+}  // extern "C"

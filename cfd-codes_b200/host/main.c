@@ -1,0 +1,229 @@
+/*
+ * host/main.c -- C host program of the B200 cavity solver: the drop-in for the reference's
+ *   "3D Lid-driven Cavity with Lattice Boltzmann Method/main.c"  ("3D:" below).
+ *
+ * Same parameter surface (now run-time flags with the reference's names and defaults, 3D:7-15, 18, 22,
+ * 43), same stdout (banner 3D:80-88, residual blocks 3D:97-98, 113-117), same convergence logic
+ * (3D:93-124) and the same Tecplot output file (3D:174, 363-382).  All lattice work goes through
+ * the C ABI of include/lbm_b200.h; this file contains no numerics except printf formatting.
+ *
+ *   lbm3d_cavity [--N 50] [--Re 100] [--UMAX 0.1] [--SAVETXT 1] [--THRESH 1E-12] [--METHOD 1]
+ *                [--GAMMA 1.0] [--DIAG 0] [--MAGIC 0.25] [--MAXITER 1E8] [--skip 500] [--gpus 1]
+ *
+ * --gpus P (the reference's THREADS knob, 3D:15) runs P z-slabs, one host thread + one context
+ * per GPU, sharing an NCCL communicator.
+ *
+ * Deviations from the reference's stdout, all deliberate:
+ *   - "Threads used:" prints the GPU count;
+ *   - LUPS is computed in double (the reference's `N3 * skip` overflows int for N >= 163, 3D:117);
+ *   - a negative equilibrium is detected at the next residual check (<= skip iterations late)
+ *     instead of immediately; message and exit status are the reference's (3D:687-692).
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "lbm_b200.h"
+
+typedef struct {
+    int N, Re, SAVETXT, METHOD, DIAG, skip, gpus;
+    double UMAX, THRESH, GAMMA, MAGIC, MAXITER;
+} options;
+
+typedef struct {
+    int rank;
+    const options *opt;
+    const unsigned char *nccl_id;
+    pthread_barrier_t *bar;
+    double *u1, *u2, *u3, *vmag; /* shared N^3 arrays (SAVETXT) */
+    int status;
+} worker;
+
+static double now(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static void die_lbm(int rc) {
+    if (rc == LBM_ERR_UNSTABLE) {
+        printf("Error: negative feq.  Therefore, unstable.\n"); /* 3D:689 */
+    } else {
+        printf("Error: %s\n", lbm_last_error());
+    }
+    fflush(stdout);
+    exit(1);
+}
+
+/* Writes the Tecplot file, 3D:363-382: i outer, j, k inner; x = y = z = linspace(0, N-1, N) (3D:175). */
+static void datwrite(const options *o, const double *u1, const double *u2, const double *u3, const double *vmag) {
+    char filename[160];
+    snprintf(filename, sizeof filename, "Solution_n=%dRe=%d_DIAG=%d_%dRT_M=%.3f.dat", o->N, o->Re, o->DIAG,
+             o->METHOD + 1, o->MAGIC); /* 3D:174 */
+    FILE *fp = fopen(filename, "w");
+    if (fp == NULL) {
+        printf("Error opening file!\n");
+        exit(1);
+    }
+    const int N = o->N;
+    const size_t N1 = (size_t)N, N2 = N1 * N1;
+    fprintf(fp, "TITLE=\"%s\" VARIABLES=\"x\", \"y\", \"z\", \"%s\", \"%s\", \"%s\", \"vmag\" ZONE T=\"%s\" I=%d J=%d K=%d F=POINT\n",
+            filename, "u", "v", "w", filename, N, N, N);
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++)
+            for (int k = 0; k < N; k++) {
+                const size_t c = (size_t)k * N2 + (size_t)j * N1 + (size_t)i; /* LU3, 3D:47 */
+                /* linspace(0, N-1, N): start + i*(stop-start)/(num-1) is exactly i (3D:328) */
+                fprintf(fp, "%.10f, %.10f, %.10f, %.10f, %.10f, %.10f, %.10f\n", (double)i, (double)j, (double)k,
+                        u1[c], u2[c], u3[c], vmag[c]);
+            }
+    fclose(fp);
+}
+
+static void *run(void *arg) {
+    worker *w = (worker *)arg;
+    const options *o = w->opt;
+    const int root = (w->rank == 0);
+    lbm_params p;
+    lbm_default_params(&p);
+    p.dim = 3; p.N = o->N; p.Re = o->Re; p.UMAX = o->UMAX; p.METHOD = o->METHOD;
+    p.GAMMA = o->GAMMA; p.MAGIC = o->MAGIC; p.DIAG = o->DIAG;
+    p.rank = w->rank; p.nranks = o->gpus; p.device = w->rank; p.track_residual = 1;
+    if (o->gpus > 1) memcpy(p.nccl_id, w->nccl_id, LBM_NCCL_ID_BYTES);
+
+    lbm_ctx *ctx = NULL;
+    int rc = lbm_create(&p, &ctx); /* allocate(); initialize();  3D:76-78 */
+    if (rc) die_lbm(rc);
+    lbm_info info;
+    lbm_get_info(ctx, &info);
+
+    if (root) { /* 3D:80-88 */
+        printf("Re =\t%d\n", o->Re);
+        printf("Re_g =\t%.3e\n", 3.0 * o->UMAX / (info.TAU - 0.5));
+        printf("U =\t%.3e\n", o->UMAX);
+        printf("N =\t%d\n", o->N);
+        printf("tau =\t%.3e\n", info.TAU);
+        printf("nu =\t%.3e\n", info.NU);
+        printf("M =\t%.3e\n", o->UMAX * sqrt(3));
+        if (o->GAMMA != 1.0) printf("M* =\t%.3e\n", o->UMAX * sqrt(3) / sqrt(o->GAMMA));
+    }
+
+    /* First iteration, 3D:94-100 */
+    double df, df0;
+    if ((rc = lbm_step(ctx, 1))) die_lbm(rc);
+    if ((rc = lbm_residual(ctx, &df0))) die_lbm(rc);
+    if (root) {
+        printf("\nIteration 0:\n");
+        printf("df:\t%.3e\n", df0);
+    }
+    df0 = 1.0 / df0;
+
+    /* Rest of iterations, 3D:103-124: iteration t is checked when t % skip == 0 */
+    double start = now();
+    const double cells = (double)o->N * (double)o->N * (double)o->N;
+    long long t = 1;
+    const long long last = (long long)o->MAXITER - 1;
+    while (t <= last) {
+        long long T = ((t + o->skip - 1) / o->skip) * o->skip; /* next check iteration */
+        if (T > last) {
+            if ((rc = lbm_step(ctx, last - t + 1))) die_lbm(rc);
+            if ((rc = lbm_sync(ctx))) die_lbm(rc);
+            break;
+        }
+        if ((rc = lbm_step(ctx, T - t + 1))) die_lbm(rc);
+        if ((rc = lbm_residual(ctx, &df))) die_lbm(rc);
+        df *= df0;
+        const double stop = now() - start;
+        if (root) {
+            printf("\nIteration %lld:\n", T);
+            printf("df/df0:\t%.3e\n", df);
+            printf("Time:\t%.3e s\n", stop);
+            printf("LUPS:\t%.3e s\n", cells * (double)o->skip / stop);
+            fflush(stdout);
+        }
+        start = now();
+        if (df < o->THRESH) break;
+        t = T + 1;
+    }
+
+    /* Output to text file, 3D:127 */
+    if (o->SAVETXT == 1) {
+        if ((rc = lbm_macrovars(ctx, w->u1, w->u2, w->u3, NULL, w->vmag))) die_lbm(rc);
+        if (o->gpus > 1) pthread_barrier_wait(w->bar);
+        if (root) datwrite(o, w->u1, w->u2, w->u3, w->vmag);
+    }
+    lbm_destroy(ctx); /* freemem(), 3D:130 */
+    w->status = 0;
+    return NULL;
+}
+
+static int flag(int argc, char **argv, int *i, const char *name, const char **val) {
+    if (strcmp(argv[*i], name) != 0) return 0;
+    if (*i + 1 >= argc) {
+        fprintf(stderr, "%s needs a value\n", name);
+        exit(2);
+    }
+    *val = argv[++*i];
+    return 1;
+}
+
+int main(int argc, char **argv) {
+    /* defaults = the reference's #defines, 3D:7-15, 18, 22, 43 */
+    options o = {.N = 50, .Re = 100, .SAVETXT = 1, .METHOD = 1, .DIAG = 0, .skip = 500, .gpus = 1,
+                 .UMAX = 0.1, .THRESH = 1E-12, .GAMMA = 1.0, .MAGIC = 0.25, .MAXITER = 1E8};
+    for (int i = 1; i < argc; i++) {
+        const char *v;
+        if (flag(argc, argv, &i, "--N", &v)) o.N = atoi(v);
+        else if (flag(argc, argv, &i, "--Re", &v)) o.Re = atoi(v);
+        else if (flag(argc, argv, &i, "--UMAX", &v)) o.UMAX = atof(v);
+        else if (flag(argc, argv, &i, "--SAVETXT", &v)) o.SAVETXT = atoi(v);
+        else if (flag(argc, argv, &i, "--THRESH", &v)) o.THRESH = atof(v);
+        else if (flag(argc, argv, &i, "--METHOD", &v)) o.METHOD = atoi(v);
+        else if (flag(argc, argv, &i, "--GAMMA", &v)) o.GAMMA = atof(v);
+        else if (flag(argc, argv, &i, "--DIAG", &v)) o.DIAG = atoi(v);
+        else if (flag(argc, argv, &i, "--MAGIC", &v)) o.MAGIC = atof(v);
+        else if (flag(argc, argv, &i, "--MAXITER", &v)) o.MAXITER = atof(v);
+        else if (flag(argc, argv, &i, "--skip", &v)) o.skip = atoi(v);
+        else if (flag(argc, argv, &i, "--gpus", &v) || flag(argc, argv, &i, "--THREADS", &v)) o.gpus = atoi(v);
+        else {
+            fprintf(stderr, "unknown argument %s\n", argv[i]);
+            return 2;
+        }
+    }
+    if (o.gpus < 1 || o.skip < 1) {
+        fprintf(stderr, "bad --gpus / --skip\n");
+        return 2;
+    }
+    printf("Threads used:\t%d\n", o.gpus); /* 3D:210 (here: GPUs) */
+
+    unsigned char id[LBM_NCCL_ID_BYTES];
+    memset(id, 0, sizeof id);
+    if (o.gpus > 1 && lbm_nccl_unique_id(id)) die_lbm(LBM_ERR_NCCL);
+
+    double *u1 = NULL, *u2 = NULL, *u3 = NULL, *vmag = NULL;
+    if (o.SAVETXT == 1) {
+        const size_t n3 = (size_t)o.N * o.N * o.N;
+        u1 = malloc(n3 * sizeof(double)); u2 = malloc(n3 * sizeof(double));
+        u3 = malloc(n3 * sizeof(double)); vmag = malloc(n3 * sizeof(double));
+        if (!u1 || !u2 || !u3 || !vmag) {
+            printf("Error allocating memory!\n"); /* 3D:339 */
+            return 1;
+        }
+    }
+    pthread_barrier_t bar;
+    pthread_barrier_init(&bar, NULL, (unsigned)o.gpus);
+    worker *ws = calloc((size_t)o.gpus, sizeof(worker));
+    pthread_t *th = calloc((size_t)o.gpus, sizeof(pthread_t));
+    for (int r = 0; r < o.gpus; r++) {
+        ws[r] = (worker){.rank = r, .opt = &o, .nccl_id = id, .bar = &bar, .u1 = u1, .u2 = u2, .u3 = u3,
+                         .vmag = vmag, .status = 1};
+        if (r > 0) pthread_create(&th[r], NULL, run, &ws[r]);
+    }
+    run(&ws[0]);
+    for (int r = 1; r < o.gpus; r++) pthread_join(th[r], NULL);
+    free(u1); free(u2); free(u3); free(vmag); free(ws); free(th);
+    return 0;
+}

@@ -18,6 +18,9 @@
  *   time <n> [threads]              the same loop, timed with omp_get_wtime;
  *                                   prints one JSON line (used as cpu_baseline
  *                                   kind "reference" by bench.py).
+ *   bench <iters> <warm> <steps> [threads]
+ *                                   `warm` untimed + `steps` timed bench steps of `iters`
+ *                                   iterations each (bench.py --impl reference); JSON line.
  *   main                            runs the reference's own main() (3D:74-132)
  *                                   in the current directory (banner, residual
  *                                   blocks, Solution_*.dat).
@@ -36,7 +39,7 @@ static void set_threads(int nt) {
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "usage: %s steps <n> <out.bin> [threads] | time <n> [threads] | main\n", argv[0]);
+        fprintf(stderr, "usage: %s steps <n> <out.bin> [threads] | time <n> [threads] | bench <iters> <warm> <steps> [threads] | main\n", argv[0]);
         return 2;
     }
     if (strcmp(argv[1], "main") == 0) return ref_main();
@@ -83,6 +86,30 @@ int main(int argc, char **argv) {
         double cells = (double)N * (double)N * (double)N;
         printf("{\"N\": %d, \"steps\": %d, \"seconds\": %.6f, \"mlups\": %.6f, \"threads\": %d}\n",
                N, n, dt, cells * n / dt / 1e6, omp_get_max_threads());
+        return 0;
+    }
+    if (strcmp(argv[1], "bench") == 0 && argc >= 5) {
+        int iters = atoi(argv[2]), warm = atoi(argv[3]), steps = atoi(argv[4]);
+        int nt = argc > 5 ? atoi(argv[5]) : 0;
+        allocate();
+        initialize();
+        set_threads(nt);
+        for (int t = 0; t < warm * iters; t++) {
+            macrocollideandstream();
+            HechtBC(f2);
+            swap(&f1, &f2);
+        }
+        double t0 = omp_get_wtime();
+        for (int t = 0; t < steps * iters; t++) {
+            macrocollideandstream();
+            HechtBC(f2);
+            swap(&f1, &f2);
+        }
+        double dt = omp_get_wtime() - t0;
+        double cells = (double)N * (double)N * (double)N;
+        printf("{\"N\": %d, \"iters_per_step\": %d, \"steps\": %d, \"warmup\": %d, \"seconds\": %.6f, "
+               "\"mlups\": %.6f, \"threads\": %d}\n",
+               N, iters, steps, warm, dt, cells * steps * iters / dt / 1e6, omp_get_max_threads());
         return 0;
     }
     fprintf(stderr, "bad arguments\n");

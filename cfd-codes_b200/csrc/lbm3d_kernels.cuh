@@ -46,8 +46,15 @@ enum Mode : int {
 
 // Kernel parameters (passed by value; lives in the constant bank).
 struct KP {
-    const double *src;   // S_old, population stride PS, plane -1 (ghost) first
-    double *dst;         // S_new, same layout
+    // Per-population base pointers, prepared by the host so that ONE 32-bit cell index addresses all
+    // 38 accesses of a cell (one IMAD.WIDE each instead of 64-bit multiply chains):
+    //   srcq[q][cell] = S_old[x - c_q][q]   (base already shifted by -(cx + cy*N + cz*N^2))
+    //   dstq[q][cell] = S_new[x][q]
+    // with cell = (kl+1)*N^2 + j*N + i (ghost plane first).  The lattices are allocated with
+    // N^2+N+1 elements of padding at both ends, so the shifted reads of box-boundary cells stay
+    // inside the allocation (their values are discarded, see k_step).
+    const double *srcq[19];
+    double *dstq[19];
     double *Fbuf;        // F buffer [q][nzl*N2] (no ghosts), may be null for MODE_STEP
     const double *side_rd;  // stale f14 of the x=N-1 face, [nzl][N] (written two iterations ago)
     double *side_wr;        // slot this iteration writes
@@ -70,7 +77,11 @@ struct KP {
 // Operation order follows 3D:224-246 (BGK) and 3D:268-302 (TRT) exactly; the only rewrites are
 // exact identities (no rounding changes): multiplying by c in {-1,0,1} becomes add/sub/skip;
 // cdotu(opp q) = -cdotu(q), so 3*cdotu and (4.5*cdotu^2 - 1.5*U2)*gammainv are shared by a pair;
-// w_q*rho has three distinct values; axis pairs reuse u*u, v*v, w*w from U2.
+// w_q*rho has three distinct values; axis pairs reuse u*u, v*v, w*w from U2; and scaling by 0.5
+// commutes with rounding (no under/overflow at these magnitudes), so
+//   OMEGA*(0.5*(a+b) - 0.5*(c+d)) == (0.5*OMEGA)*((a+b) - (c+d))   bit for bit (3D:293-299).
+// checkfeq (feq < 0.0, 3D:688) is evaluated on the sign bits: the OR of the high words is
+// negative iff some feq has its sign bit set (feq = -0.0 cannot occur for finite rho != 0).
 template <int METHOD>
 __device__ __forceinline__ bool collide(double (&f)[Q], const KP &p) {
     // 3D:268-270 / 3D:225-235 (the += loop visits q = 0..18: same order, zero terms are exact)
@@ -97,11 +108,12 @@ __device__ __forceinline__ bool collide(double (&f)[Q], const KP &p) {
     const double U2 = (uu + vv) + ww;   // 3D:240, 284
     const double k15 = 1.5 * U2;
     const double wr0 = LBM_W0 * rho, wr1 = LBM_W1 * rho, wr2 = LBM_W2 * rho;  // `w * rho * (...)`, 3D:166
-    bool neg = false;
+    int negbits = 0;
+    const double homega = 0.5 * p.omega, homegam = 0.5 * p.omegam;  // exact
 
     {   // rest population, cdotu = 0: feq = w*rho*(1.0 + (0 - 1.5*U2)*gammainv)
         const double fe = wr0 * (1.0 + (-k15) * p.gammainv);
-        neg |= (fe < 0.0);
+        negbits |= __double2hiint(fe);
         if (METHOD == 1) f[0] = f[0] - p.omega * (f[0] - fe);        // 3D:286
         else             f[0] = p.omomega * f[0] + p.omega * fe;     // 3D:246
     }
@@ -111,14 +123,10 @@ __device__ __forceinline__ bool collide(double (&f)[Q], const KP &p) {
         const double E = (4.5 * (cc) - k15) * p.gammainv;                                            \
         const double fe1 = (wr) * ((1.0 + t3) + E);                                                  \
         const double fe2 = (wr) * ((1.0 - t3) + E);                                                  \
-        neg |= (fe1 < 0.0) | (fe2 < 0.0);                                                            \
+        negbits |= __double2hiint(fe1) | __double2hiint(fe2);                                        \
         if (METHOD == 1) { /* 3D:293-302 */                                                          \
-            double fplus = 0.5 * (f[q] + f[q + 1]);                                                  \
-            double fminus = 0.5 * (f[q] - f[q + 1]);                                                 \
-            const double feqplus = 0.5 * (fe1 + fe2);                                                \
-            const double feqminus = 0.5 * (fe1 - fe2);                                               \
-            fplus = p.omega * (fplus - feqplus);                                                     \
-            fminus = p.omegam * (fminus - feqminus);                                                 \
+            const double fplus = homega * ((f[q] + f[q + 1]) - (fe1 + fe2));                         \
+            const double fminus = homegam * ((f[q] - f[q + 1]) - (fe1 - fe2));                       \
             const double a = f[q] - fplus - fminus;                                                  \
             const double b = f[q + 1] - fplus + fminus;                                              \
             f[q] = a;                                                                                \
@@ -138,7 +146,7 @@ __device__ __forceinline__ bool collide(double (&f)[Q], const KP &p) {
     { const double c = u - w; LBM_PAIR(15, c, c * c, wr2) }
     { const double c = v - w; LBM_PAIR(17, c, c * c, wr2) }
 #undef LBM_PAIR
-    return neg;
+    return negbits < 0;
 }
 
 // ---- wall / lid / edge / corner rules (HechtBC, 3D:385-675) --------------------------------------
@@ -238,38 +246,40 @@ __global__ void __launch_bounds__(256, 2) k_step(const __grid_constant__ KP p) {
         const int by = (j == 0) ? 1 : ((j == p.M) ? 2 : 0);
         const int bz = (kg == 0) ? 1 : ((kg == p.Mz) ? 2 : 0);
         const int cls = LBM_CLS(bx, by, bz);
-        const long long N1 = p.N, N2 = p.N2, PS = p.PS;
-        const long long rowcell = (long long)j * N1 + i;
-        const double *s = p.src + ((long long)(kl + 1) * N2 + rowcell);
+        const int N1 = p.N;
+        const int rowcell = j * N1 + i;
+        const int cell = (kl + 1) * (int)p.N2 + rowcell;   // < 2^31 (checked by the host)
 
         double f[Q];
-        // 1. pull.  Source x - c_q; outside the box the reference never writes the slot, which
-        //    therefore still holds w[q] (buried slots) or is overwritten by the rule below.
-#define LBM_PULL(q, cx, cy, cz, wq)                                                                  \
-        {                                                                                            \
-            const bool in = !((cx == 1 && bx == 1) || (cx == -1 && bx == 2) || (cy == 1 && by == 1) || \
-                              (cy == -1 && by == 2) || (cz == 1 && bz == 1) || (cz == -1 && bz == 2)); \
-            f[q] = in ? s[(long long)(q) * PS - ((long long)(cx) + (long long)(cy) * N1 + (long long)(cz) * N2)] \
-                      : (wq);                                                                        \
-        }
+        // 1. pull: unconditional, coalesced 8-byte loads through the pre-shifted bases.
+#define LBM_PULL(q, cx, cy, cz, wq) f[q] = p.srcq[q][cell];
         LBM_D3Q19_VEL(LBM_PULL)
 #undef LBM_PULL
 
-        // 2. boundary rule of this cell's class
+        // 2. boundary cells only
         if (cls != 0) {
+            // A source outside the box: the reference never writes that slot, which therefore still
+            // holds w[q] (buried slots) or is overwritten by the rule below.  The value
+            // loaded above (a wrapped neighbour or padding) is discarded.
+#define LBM_FIX(q, cx, cy, cz, wq)                                                                   \
+            if ((cx == 1 && bx == 1) || (cx == -1 && bx == 2) || (cy == 1 && by == 1) ||             \
+                (cy == -1 && by == 2) || (cz == 1 && bz == 1) || (cz == -1 && bz == 2))              \
+                f[q] = (wq);
+            LBM_D3Q19_VEL(LBM_FIX)
+#undef LBM_FIX
             const bool xm_face = (cls == LBM_CLS(2, 0, 0));
             // stale f14 (3D:421): at x = N-1 the rule reads population 14 before assigning it; the
             // reference finds there what HechtBC wrote into the same buffer two iterations ago.
-            if (xm_face) f[14] = p.side_rd[(long long)kl * N1 + j];
+            if (xm_face) f[14] = p.side_rd[kl * N1 + j];
             apply_boundary(f, cls, p);
             if (MODE != MODE_MATERIALISE) {
-                if (xm_face) p.side_wr[(long long)kl * N1 + j] = f[14];
+                if (xm_face) p.side_wr[kl * N1 + j] = f[14];
             }
         }
 
         // f == the reference's f2[x][:] after HechtBC of this iteration
         if (MODE != MODE_STEP) {
-            double *F = p.Fbuf + ((long long)kl * N2 + rowcell);
+            double *F = p.Fbuf + ((long long)kl * p.N2 + rowcell);
             if (MODE == MODE_STEP_DIFF_STOREF) {
 #pragma unroll
                 for (int q = 0; q < Q; q++) {
@@ -285,9 +295,8 @@ __global__ void __launch_bounds__(256, 2) k_step(const __grid_constant__ KP p) {
         if (MODE != MODE_MATERIALISE) {
             const bool neg = collide<METHOD>(f, p);
             if (neg) atomicOr(p.flag, 1);
-            double *d = p.dst + ((long long)(kl + 1) * N2 + rowcell);
 #pragma unroll
-            for (int q = 0; q < Q; q++) d[(long long)q * PS] = f[q];
+            for (int q = 0; q < Q; q++) p.dstq[q][cell] = f[q];
         }
     }
 
@@ -322,9 +331,9 @@ __global__ void __launch_bounds__(256, 2) k_collide_cells(const __grid_constant_
     }
     const bool neg = collide<METHOD>(f, p);
     if (neg) atomicOr(p.flag, 1);
-    double *d = p.dst + ((long long)(kl + 1) * p.N2 + rowcell);
+    const int cell = (kl + 1) * (int)p.N2 + (int)rowcell;
 #pragma unroll
-    for (int q = 0; q < Q; q++) d[(long long)q * p.PS] = f[q];
+    for (int q = 0; q < Q; q++) p.dstq[q][cell] = f[q];
 }
 
 // Fill the F buffer with the initial distributions f = w[q] (3D:192-205).

@@ -96,7 +96,9 @@ struct lbm_ctx {
     long long N2 = 0, PS = 0, FS = 0;
     double NU, TAU, OMEGA, OMEGAm, OmOMEGA, gammainv, ulid, vlid, wlid;
 
-    double *lat[2] = {nullptr, nullptr};  // post-collision lattices, ghost plane first
+    double *lat_alloc[2] = {nullptr, nullptr};
+    long long pad = 0;                    // elements of padding before/after each lattice
+    double *lat[2] = {nullptr, nullptr};  // post-collision lattices (= lat_alloc + pad), ghost plane first
     int cur = 0;                          // lat[cur] holds S of the latest iteration
     double *Fbuf = nullptr;               // the reference's f2 of the latest iteration when f_valid
     bool f_valid = false;
@@ -129,22 +131,36 @@ static int dev_alloc(lbm_ctx *c, T **p, long long count) {
 
 static void choose_block(const lbm_ctx *c, dim3 *blk, dim3 *grd_xy) {
     int bx = c->block_x, by = c->block_y;
+    // 128-thread blocks measured best on B200 (profiles/): 4-5 blocks per SM at <= 128 registers.
     if (bx <= 0) {
         bx = ((c->N + 31) / 32) * 32;
-        if (bx > 256) bx = 256;
-        // prefer a divisor of the row so that no lanes idle (N = 512 -> 256, N = 320 -> 160)
-        if (c->N > 256) {
-            for (int cand = 256; cand >= 64; cand -= 32)
+        if (bx > 128) bx = 128;
+        // prefer a divisor of the row so that no lanes idle (N = 512 -> 128, N = 320 -> 64)
+        if (c->N > 128) {
+            for (int cand = 128; cand >= 64; cand -= 32)
                 if (c->N % cand == 0) { bx = cand; break; }
         }
     }
     if (by <= 0) {
-        by = 256 / bx;
+        by = 128 / bx;
         if (by < 1) by = 1;
         if (by > c->N) by = c->N;
     }
     *blk = dim3(bx, by, 1);
     *grd_xy = dim3((c->N + bx - 1) / bx, (c->N + by - 1) / by, 1);
+}
+
+// velocities 3D:36-38
+static const int CX19[19] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 0, 0, 1, -1, 1, -1, 0, 0};
+static const int CY19[19] = {0, 0, 0, 1, -1, 0, 0, 1, -1, 0, 0, 1, -1, -1, 1, 0, 0, 1, -1};
+static const int CZ19[19] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 0, 0, -1, 1, -1, 1};
+
+static void kp_set_lattices(const lbm_ctx *c, lbm3d::KP *p, const double *src, double *dst) {
+    for (int q = 0; q < lbm3d::Q; q++) {
+        const long long shift = (long long)CX19[q] + (long long)CY19[q] * c->N + (long long)CZ19[q] * c->N2;
+        p->srcq[q] = src ? src + (long long)q * c->PS - shift : nullptr;
+        p->dstq[q] = dst ? dst + (long long)q * c->PS : nullptr;
+    }
 }
 
 static lbm3d::KP make_kp(const lbm_ctx *c) {
@@ -235,8 +251,7 @@ static int run_iteration(lbm_ctx *c, int mode) {
     // iteration index t = c->steps (real step) or c->steps - 1 (re-materialising the last one)
     const long long t = real ? c->steps : c->steps - 1;
     const int src_i = real ? c->cur : (c->cur ^ 1);
-    p.src = c->lat[src_i];
-    p.dst = c->lat[src_i ^ 1];
+    kp_set_lattices(c, &p, c->lat[src_i], c->lat[src_i ^ 1]);
     const long long side_n = (long long)c->nzl * c->N;
     p.side_rd = c->side + ((t + 1) % 3) * side_n;  // written by iteration t-2
     p.side_wr = c->side + (t % 3) * side_n;
@@ -339,7 +354,7 @@ int lbm_destroy(lbm_ctx *c) {
     if (c->s_main) cudaStreamSynchronize(c->s_main);
     if (c->s_halo) cudaStreamSynchronize(c->s_halo);
     if (c->comm) g_nccl.CommDestroy(c->comm);
-    cudaFree(c->lat[0]); cudaFree(c->lat[1]); cudaFree(c->Fbuf); cudaFree(c->side);
+    cudaFree(c->lat_alloc[0]); cudaFree(c->lat_alloc[1]); cudaFree(c->Fbuf); cudaFree(c->side);
     cudaFree(c->partials); cudaFree(c->d_red); cudaFree(c->d_flag);
     for (int a = 0; a < 5; a++) cudaFree(c->d_out[a]);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -363,7 +378,7 @@ static int create3d(lbm_ctx *c) {
     if (c->nzl < 1) return fail(LBM_ERR_INVALID, "rank %d of %d owns no plane of N=%d", p.rank, p.nranks, p.N);
     c->PS = (long long)(c->nzl + 2) * c->N2;
     c->FS = (long long)c->nzl * c->N2;
-    if (c->FS >= (1LL << 31)) return fail(LBM_ERR_INVALID, "more than 2^31 cells per GPU");
+    if (c->PS >= (1LL << 31)) return fail(LBM_ERR_INVALID, "more than 2^31 cells per GPU");
 
     // derived constants in the reference's macro order (3D:19-23, 30, 40) so the doubles are
     // bit-identical to gcc's constant folding
@@ -384,8 +399,13 @@ static int create3d(lbm_ctx *c) {
     c->vlid = 0.0;
 
     int rc;
-    if ((rc = dev_alloc(c, &c->lat[0], (long long)lbm3d::Q * c->PS))) return rc;
-    if ((rc = dev_alloc(c, &c->lat[1], (long long)lbm3d::Q * c->PS))) return rc;
+    c->pad = ((c->N2 + c->N + 1 + 15) / 16) * 16;  // shifted pulls of box-boundary cells stay inside the allocation
+    for (int l = 0; l < 2; l++) {
+        if ((rc = dev_alloc(c, &c->lat_alloc[l], (long long)lbm3d::Q * c->PS + 2 * c->pad))) return rc;
+        CK(cudaMemsetAsync(c->lat_alloc[l], 0, (size_t)c->pad * sizeof(double), c->s_main));
+        CK(cudaMemsetAsync(c->lat_alloc[l] + c->pad + (long long)lbm3d::Q * c->PS, 0, (size_t)c->pad * sizeof(double), c->s_main));
+        c->lat[l] = c->lat_alloc[l] + c->pad;
+    }
     const long long side_n = (long long)c->nzl * c->N;
     if ((rc = dev_alloc(c, &c->side, 3 * side_n))) return rc;
     if ((rc = dev_alloc(c, &c->d_red, 2))) return rc;
@@ -404,7 +424,7 @@ static int create3d(lbm_ctx *c) {
     choose_block(c, &blk, &gxy);
     for (int l = 0; l < 2; l++) {
         lbm3d::KP kp = make_kp(c);
-        kp.dst = c->lat[l];
+        kp_set_lattices(c, &kp, nullptr, c->lat[l]);
         kp.Fbuf = nullptr;
         dim3 grid(gxy.x, gxy.y, c->nzl + 2);
         if (p.METHOD == 1) lbm3d::k_collide_cells<1><<<grid, blk, 0, c->s_main>>>(kp, 1);
@@ -614,7 +634,7 @@ int lbm_set_f(lbm_ctx *c, const double *host_f, const double *host_f_prev) {
     dim3 blk, gxy;
     choose_block(c, &blk, &gxy);
     lbm3d::KP kp = make_kp(c);
-    kp.dst = c->lat[c->cur];
+    kp_set_lattices(c, &kp, nullptr, c->lat[c->cur]);
     dim3 grid(gxy.x, gxy.y, c->nzl);
     if (c->prm.METHOD == 1) lbm3d::k_collide_cells<1><<<grid, blk, 0, c->s_main>>>(kp, 0);
     else                    lbm3d::k_collide_cells<0><<<grid, blk, 0, c->s_main>>>(kp, 0);

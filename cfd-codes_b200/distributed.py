@@ -1,0 +1,71 @@
+"""Host-side plumbing for multi-GPU runs: one process per GPU (torchrun), `torch.distributed` for the
+rendezvous only.  The data path (halo exchange of the five face-crossing populations per slab face,
+residual all-reduce) is NCCL inside liblbm_b200.so; nothing here touches the lattice.
+
+The reference's only distributed program is the 2D one (MPI row slabs, 2D main.cpp:97-125, 208-270);
+this is the same decomposition along the slowest axis of the 3D lattice (z, LU4 main.c:48)."""
+import os
+
+import numpy as np
+
+from . import NCCL_ID_BYTES, nccl_unique_id, slab_range
+
+
+def env_rank():
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def init_process_group(backend=None):
+    """Rendezvous over 127.0.0.1 (the container hostname may not resolve)."""
+    import torch
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    if not dist.is_initialized():
+        if backend is None:
+            backend = "cpu:gloo,cuda:nccl" if torch.cuda.is_available() else "gloo"
+        dist.init_process_group(backend)
+    return dist
+
+
+def broadcast_nccl_id(make_id=nccl_unique_id):
+    """Rank 0 creates the ncclUniqueId (through the C ABI), everybody receives the 128 bytes."""
+    import torch
+    import torch.distributed as dist
+    t = torch.zeros(NCCL_ID_BYTES, dtype=torch.uint8)
+    if dist.get_rank() == 0:
+        raw = make_id()
+        assert len(raw) == NCCL_ID_BYTES
+        t.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+    dist.broadcast(t, 0)
+    return bytes(t.tolist())
+
+
+def gather_slabs(local, n_slowest, plane_elems, nfields):
+    """Gather compact per-rank slabs [nfields][k1-k0][plane] onto rank 0 as [nfields][n][plane]
+    (the reference's LU4 / LU3 order).  Returns the full array on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    k0, k1 = slab_range(n_slowest, rank, world)
+    local = np.ascontiguousarray(local, dtype=np.float64).reshape(nfields, k1 - k0, plane_elems)
+    if rank == 0:
+        full = np.empty((nfields, n_slowest, plane_elems), dtype=np.float64)
+        full[:, k0:k1] = local
+        for r in range(1, world):
+            a, b = slab_range(n_slowest, r, world)
+            buf = torch.empty(nfields * (b - a) * plane_elems, dtype=torch.float64)
+            dist.recv(buf, src=r)
+            full[:, a:b] = buf.numpy().reshape(nfields, b - a, plane_elems)
+        return full
+    dist.send(torch.from_numpy(local.reshape(-1)), dst=0)
+    return None
+
+
+def allreduce_max(x):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

@@ -285,3 +285,127 @@ def run_to_convergence(sim, THRESH=1e-12, skip=500, MAXITER=int(1e8), log=None):
         if df < THRESH:
             break
     return t, df
+
+
+class Cavity2D:
+    """D2Q9 N x M cavity, the variant of the same kernel named by BASELINE config 5; parameters
+    as the reference's 2D program (2D main.cpp:12-17, 25): Re, N (width), M (height), Ulid, MAGIC.
+
+        reference (main.cpp)                                   here
+        -----------------------------------------------------  ----------------------------
+        one sweep of streamCollide over all rows   2D:160-178  Cavity2D.step(n)
+        macroVars(...) + convergence(...)          2D:419-478  Cavity2D.residual()
+        dist (LU3 layout 9N*j + N*k + i)           2D:276-278  Cavity2D.dist()
+        u, v, rho arrays / outputScalar            2D:482-495  Cavity2D.macro(), Cavity2D.output_bin()
+
+    The update is the time-consistent two-lattice version of the reference's in-place sweep
+    (DESIGN.md 7); residual() is the change of (u, v, rho) since the previous residual() call."""
+
+    Q = 9
+
+    def __init__(self, N=100, M=300, Re=100.0, Ulid=0.1, MAGIC=0.25, rank=0, nranks=1, device=-1, nccl_id=None):
+        self._h = None
+        L = load_library()
+        p = default_params()
+        p.dim, p.N, p.M, p.Re, p.UMAX, p.METHOD, p.MAGIC = 2, N, M, Re, Ulid, 1, MAGIC
+        p.rank, p.nranks, p.device, p.track_residual = rank, nranks, device, 0
+        if nranks > 1:
+            if nccl_id is None or len(nccl_id) != NCCL_ID_BYTES:
+                raise ValueError("nranks > 1 needs the shared nccl_unique_id() bytes")
+            C.memmove(p.nccl_id, nccl_id, NCCL_ID_BYTES)
+        self.params, self.N, self.M = p, N, M
+        h = C.c_void_p()
+        _check(L.lbm_create(C.byref(p), C.byref(h)))
+        self._h, self._L = h, L
+
+    def step(self, n=1):
+        _check(self._L.lbm_step(self._h, n))
+
+    def step_timed(self, n):
+        ms = C.c_float()
+        _check(self._L.lbm_step_timed(self._h, n, C.byref(ms)))
+        return ms.value
+
+    def residual(self):
+        out = C.c_double()
+        _check(self._L.lbm_residual(self._h, C.byref(out)))
+        return out.value
+
+    def sync(self):
+        _check(self._L.lbm_sync(self._h))
+
+    def dist(self, out=None):
+        if out is None:
+            out = np.zeros(9 * self.N * self.M, dtype=np.float64)
+        _check(self._L.lbm_get_f(self._h, _ptr(out)))
+        return out
+
+    def set_dist(self, d):
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        _check(self._L.lbm_set_f(self._h, _ptr(d), None))
+
+    def macro(self, out=None):
+        n = self.N * self.M
+        if out is None:
+            out = {k: np.zeros(n, dtype=np.float64) for k in ("u", "v", "rho")}
+        _check(self._L.lbm_macrovars(self._h, _ptr(out["u"]), _ptr(out["v"]), None, _ptr(out["rho"]), None))
+        return out
+
+    def info(self):
+        i = LbmInfo()
+        _check(self._L.lbm_get_info(self._h, C.byref(i)))
+        return {k: getattr(i, k) for k, _ in LbmInfo._fields_}
+
+    def set_option(self, key, value):
+        _check(self._L.lbm_set_option(self._h, key.encode(), int(value)))
+
+    def output_bin(self, directory=".", mv=None):
+        """The reference's output files `Re=%.0f_N=%d_M=%d_{x,y,u,v,rho}.bin` (2D:190-202, 482-495):
+        raw little-endian doubles, M rows x N columns; x = 0.5 + i, y = 0.5 + j (2D:146-152)."""
+        mv = mv or self.macro()
+        p = self.params
+        j, i = np.meshgrid(np.arange(self.M, dtype=np.float64), np.arange(self.N, dtype=np.float64), indexing="ij")
+        fields = dict(x=0.5 + i, y=0.5 + j, u=mv["u"], v=mv["v"], rho=mv["rho"])
+        paths = []
+        for name, a in fields.items():
+            path = os.path.join(directory, "Re=%.0f_N=%d_M=%d_%s.bin" % (p.Re, p.N, p.M, name))
+            np.ascontiguousarray(a, dtype="<f8").tofile(path)
+            paths.append(path)
+        return paths
+
+    def close(self):
+        if self._h:
+            self._L.lbm_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def run_to_convergence_2d(sim, THRESH=2e-9, prntInt=1000, MAXITER=int(1e6), log=None):
+    """The 2D reference's loop (2D:160-187, 452-478): macroVars/convergence after iterations
+    1, prntInt+1, 2*prntInt+1, ...; df0 from the first check.  Returns (t of the last check, df)."""
+    sim.step(1)
+    d0 = sim.residual()
+    if log:
+        log("Iteration\tdf/df0\t\tMLUPS")
+        log("%.3e\t%.3e" % (0.0, 1.0))
+    t, df = 0, 1.0
+    while t + prntInt < MAXITER:
+        sim.step(prntInt)
+        t += prntInt
+        df = sim.residual() / d0
+        if log:
+            log("%.3e\t%.3e" % (float(t), df))
+        if df < THRESH:
+            break
+    return t, df

@@ -14,6 +14,7 @@
 
 #include "../../include/lbm_b200.h"
 #include "lbm3d_kernels.cuh"
+#include "lbm2d_kernels.cuh"
 
 // ---- error plumbing ------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -111,6 +112,12 @@ struct lbm_ctx {
     double *h_pin = nullptr;                                         // pinned: [0..1] sums, [2] flag (as double slot)
     bool residual_ready = false;
     bool unstable = false;
+
+    // dim = 2 (D2Q9): N x M, row slabs [j0, j1); lat[] = [9][nyl+2][N]; macroVars state u2/v2/rho2
+    int M2 = 0, nyl = 0, j0 = 0, j1 = 0;
+    double *u2 = nullptr, *v2 = nullptr, *rho2 = nullptr;
+    double *out2[3] = {nullptr, nullptr, nullptr};
+    double lid6 = 0.0;
 
     long long steps = 0, launches = 0, bytes = 0;
     int block_x = 0, block_y = 0;
@@ -324,6 +331,211 @@ static int poll_flag(lbm_ctx *c) {
     return LBM_OK;
 }
 
+
+// =====================================================================================================
+// dim = 2: D2Q9 cavity (2D main.cpp).  Row slabs along y, ghost row below/above, same stream/event
+// scheme as the 3D path; exchanged populations are the reference's own (2D:208-270): {2,5,6} upward,
+// {4,7,8} downward, N doubles each.
+// =====================================================================================================
+static const int CX9[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};   // implied by the pulls 2D:292-348
+static const int CY9[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+static const int Q2_UP[3] = {2, 5, 6};
+static const int Q2_DN[3] = {4, 7, 8};
+
+static lbm2d::KP2 make_kp2(const lbm_ctx *c, const double *src, double *dst) {
+    lbm2d::KP2 p;
+    memset(&p, 0, sizeof(p));
+    for (int k = 0; k < 9; k++) {
+        const long long shift = (long long)CX9[k] + (long long)CY9[k] * c->N;
+        p.srcq[k] = src ? src + (long long)k * c->PS - shift : nullptr;
+        p.own[k] = src ? src + (long long)k * c->PS : nullptr;
+        p.dstq[k] = dst ? dst + (long long)k * c->PS : nullptr;
+    }
+    p.u = c->u2; p.v = c->v2; p.rho = c->rho2;
+    p.partials = c->partials;
+    p.N = c->N; p.M = c->M2; p.nyl = c->nyl; p.j0 = c->j0;
+    p.jl0 = 0; p.jstride = 1; p.partial_base = 0;
+    p.omega = c->OMEGA; p.homega = 0.5 * c->OMEGA; p.homegam = 0.5 * c->OMEGAm;  // 2D:365-366
+    p.lid6 = c->lid6;
+    return p;
+}
+
+static int block2d(const lbm_ctx *c) {
+    if (c->block_x > 0) return c->block_x;
+    int bx = ((c->N + 31) / 32) * 32;
+    if (bx > 128) bx = 128;
+    return bx;
+}
+
+static int halo_exchange2d(lbm_ctx *c, double *L, cudaStream_t st) {
+    const int r = c->prm.rank, P = c->prm.nranks;
+    const size_t n = (size_t)c->N;
+    NK(g_nccl.GroupStart());
+    for (int a = 0; a < 3; a++) {
+        if (r + 1 < P) {
+            NK(g_nccl.Send(L + (long long)Q2_UP[a] * c->PS + (long long)c->nyl * c->N, n, ncclDouble, r + 1, c->comm, st));
+            NK(g_nccl.Recv(L + (long long)Q2_DN[a] * c->PS + (long long)(c->nyl + 1) * c->N, n, ncclDouble, r + 1, c->comm, st));
+        }
+        if (r > 0) {
+            NK(g_nccl.Send(L + (long long)Q2_DN[a] * c->PS + (long long)c->N, n, ncclDouble, r - 1, c->comm, st));
+            NK(g_nccl.Recv(L + (long long)Q2_UP[a] * c->PS, n, ncclDouble, r - 1, c->comm, st));
+        }
+    }
+    NK(g_nccl.GroupEnd());
+    return LBM_OK;
+}
+
+static int create2d(lbm_ctx *c) {
+    const lbm_params &p = c->prm;
+    c->N = p.N;
+    c->M2 = p.M;
+    c->j0 = (int)((long long)p.rank * p.M / p.nranks);
+    c->j1 = (int)((long long)(p.rank + 1) * p.M / p.nranks);
+    c->nyl = c->j1 - c->j0;
+    c->k0 = c->j0; c->k1 = c->j1;
+    if (c->nyl < 1) return fail(LBM_ERR_INVALID, "rank %d of %d owns no row of M=%d", p.rank, p.nranks, p.M);
+    c->N2 = p.N;                                 // "plane" = one row
+    c->PS = (long long)(c->nyl + 2) * c->N;
+    c->FS = (long long)c->nyl * c->N;
+    if (c->PS >= (1LL << 31)) return fail(LBM_ERR_INVALID, "more than 2^31 cells per GPU");
+    // 2D:22-26, evaluated in the same order
+    c->NU = p.UMAX * p.N / p.Re;
+    c->TAU = c->NU * 3.0 + 0.5;
+    c->OMEGA = 1.0 / c->TAU;
+    c->OMEGAm = 1.0 / (0.5 + (p.MAGIC / (c->TAU - 0.5)));
+    c->OmOMEGA = 1.0 - c->OMEGA;
+    c->gammainv = 1.0;
+    c->ulid = p.UMAX; c->vlid = 0.0; c->wlid = 0.0;
+    c->lid6 = 6.0 * LBM2_WD * p.UMAX;            // 2D:354
+
+    int rc;
+    c->pad = ((c->N + 1 + 15) / 16) * 16;
+    const long long tot = 9LL * c->PS + 2 * c->pad;
+    for (int l = 0; l < 2; l++) {
+        if ((rc = dev_alloc(c, &c->lat_alloc[l], tot))) return rc;
+        CK(cudaMemsetAsync(c->lat_alloc[l], 0, (size_t)tot * sizeof(double), c->s_main));  // dist = 0, 2D:127,138
+        c->lat[l] = c->lat_alloc[l] + c->pad;
+    }
+    if ((rc = dev_alloc(c, &c->u2, c->FS))) return rc;
+    if ((rc = dev_alloc(c, &c->v2, c->FS))) return rc;
+    if ((rc = dev_alloc(c, &c->rho2, c->FS))) return rc;
+    if ((rc = dev_alloc(c, &c->d_red, 2))) return rc;
+    if ((rc = dev_alloc(c, &c->d_flag, 1))) return rc;
+    CK(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->s_main));
+    CK(cudaMemsetAsync(c->d_red, 0, 2 * sizeof(double), c->s_main));
+    CK(cudaMemsetAsync(c->u2, 0, (size_t)c->FS * sizeof(double), c->s_main));   // u = v = 0, rho = 1, 2D:128-133
+    CK(cudaMemsetAsync(c->v2, 0, (size_t)c->FS * sizeof(double), c->s_main));
+    lbm3d::k_fill<<<(unsigned)((c->FS + 255) / 256), 256, 0, c->s_main>>>(c->rho2, c->FS, 1.0);
+    c->launches++;
+    CK(cudaMallocHost((void **)&c->h_pin, 4 * sizeof(double)));
+    const int bx = block2d(c);
+    c->npartials = (long long)((c->N + bx - 1) / bx) * c->nyl;
+    if ((rc = dev_alloc(c, &c->partials, c->npartials))) return rc;
+    c->cur = 0;
+    c->steps = 0;
+    CK(cudaStreamSynchronize(c->s_main));
+    return LBM_OK;
+}
+
+static int step2d(lbm_ctx *c, long long n) {
+    const int bx = block2d(c);
+    const unsigned gx = (unsigned)((c->N + bx - 1) / bx);
+    const bool multi = c->prm.nranks > 1;
+    for (long long t = 0; t < n; t++) {
+        lbm2d::KP2 p = make_kp2(c, c->lat[c->cur], c->lat[c->cur ^ 1]);
+        if (multi && c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
+        if (!multi) {
+            lbm2d::k2_step<<<dim3(gx, c->nyl), bx, 0, c->s_main>>>(p);
+            c->launches++;
+        } else {
+            const int nb = c->nyl >= 2 ? 2 : 1;
+            p.jl0 = 0; p.jstride = c->nyl >= 2 ? c->nyl - 1 : 1;
+            lbm2d::k2_step<<<dim3(gx, nb), bx, 0, c->s_main>>>(p);
+            c->launches++;
+            CK(cudaEventRecord(c->ev_bnd, c->s_main));
+            CK(cudaStreamWaitEvent(c->s_halo, c->ev_bnd, 0));
+            int rc = halo_exchange2d(c, c->lat[c->cur ^ 1], c->s_halo);
+            if (rc) return rc;
+            CK(cudaEventRecord(c->ev_halo, c->s_halo));
+            c->halo_pending = true;
+            if (c->nyl > 2) {
+                p.jl0 = 1; p.jstride = 1;
+                lbm2d::k2_step<<<dim3(gx, c->nyl - 2), bx, 0, c->s_main>>>(p);
+                c->launches++;
+            }
+        }
+        c->cur ^= 1;
+        c->steps++;
+    }
+    CK(cudaGetLastError());
+    return LBM_OK;
+}
+
+// macroVars + convergence (2D:419-478): change of (u, v, rho) since the previous call
+static int residual2d(lbm_ctx *c, double *out) {
+    const int bx = block2d(c);
+    const unsigned gx = (unsigned)((c->N + bx - 1) / bx);
+    if ((long long)gx * c->nyl > c->npartials) {
+        cudaFree(c->partials); c->bytes -= c->npartials * 8; c->partials = nullptr;
+        c->npartials = (long long)gx * c->nyl;
+        int rc = dev_alloc(c, &c->partials, c->npartials);
+        if (rc) return rc;
+    }
+    lbm2d::KP2 p = make_kp2(c, c->lat[c->cur], nullptr);
+    lbm2d::k2_macro<true><<<dim3(gx, c->nyl), bx, 0, c->s_main>>>(p);
+    lbm3d::k_sum_partials<<<1, 1024, 0, c->s_main>>>(c->partials, (long long)gx * c->nyl, c->d_red);
+    c->launches += 2;
+    CK(cudaGetLastError());
+    const double *src = c->d_red;
+    if (c->prm.nranks > 1) {
+        NK(g_nccl.AllReduce(c->d_red, c->d_red + 1, 1, ncclDouble, ncclSum, c->comm, c->s_main));  // 2D:457
+        src = c->d_red + 1;
+    }
+    CK(cudaMemcpyAsync(c->h_pin, src, sizeof(double), cudaMemcpyDeviceToHost, c->s_main));
+    CK(cudaStreamSynchronize(c->s_main));
+    *out = sqrt(c->h_pin[0]);  // 2D:460
+    return LBM_OK;
+}
+
+// dist in the reference's layout LU3(i,j,k) = 9N*j + N*k + i (2D:276-278)
+static int copy_dist2d(lbm_ctx *c, double *host, bool to_host) {
+    const long long hj0 = c->host_local ? 0 : c->j0;
+    for (int k = 0; k < 9; k++) {
+        double *h = host + hj0 * 9 * c->N + (long long)k * c->N;
+        double *d = c->lat[c->cur] + (long long)k * c->PS + c->N;
+        if (to_host)
+            CK(cudaMemcpy2DAsync(h, (size_t)9 * c->N * 8, d, (size_t)c->N * 8, (size_t)c->N * 8, (size_t)c->nyl,
+                                 cudaMemcpyDeviceToHost, c->s_main));
+        else
+            CK(cudaMemcpy2DAsync(d, (size_t)c->N * 8, h, (size_t)9 * c->N * 8, (size_t)c->N * 8, (size_t)c->nyl,
+                                 cudaMemcpyHostToDevice, c->s_main));
+    }
+    CK(cudaStreamSynchronize(c->s_main));
+    return LBM_OK;
+}
+
+static int macrovars2d(lbm_ctx *c, double *u, double *v, double *rho, double *vmag) {
+    int rc;
+    for (int a = 0; a < 3; a++)
+        if (!c->out2[a]) { if ((rc = dev_alloc(c, &c->out2[a], c->FS))) return rc; }
+    const int bx = block2d(c);
+    const unsigned gx = (unsigned)((c->N + bx - 1) / bx);
+    lbm2d::KP2 p = make_kp2(c, c->lat[c->cur], nullptr);
+    p.u = c->out2[0]; p.v = c->out2[1]; p.rho = c->out2[2];
+    lbm2d::k2_macro<false><<<dim3(gx, c->nyl), bx, 0, c->s_main>>>(p);
+    c->launches++;
+    CK(cudaGetLastError());
+    const long long off = c->host_local ? 0 : (long long)c->j0 * c->N;
+    double *host[3] = {u, v, rho};
+    for (int a = 0; a < 3; a++)
+        if (host[a])
+            CK(cudaMemcpyAsync(host[a] + off, c->out2[a], (size_t)c->FS * 8, cudaMemcpyDeviceToHost, c->s_main));
+    CK(cudaStreamSynchronize(c->s_main));
+    if (vmag && u && v)
+        for (long long n = 0; n < c->FS; n++) vmag[off + n] = sqrt(u[off + n] * u[off + n] + v[off + n] * v[off + n]);
+    return LBM_OK;
+}
+
 // ---- C ABI ---------------------------------------------------------------------------------------
 extern "C" {
 
@@ -357,6 +569,8 @@ int lbm_destroy(lbm_ctx *c) {
     cudaFree(c->lat_alloc[0]); cudaFree(c->lat_alloc[1]); cudaFree(c->Fbuf); cudaFree(c->side);
     cudaFree(c->partials); cudaFree(c->d_red); cudaFree(c->d_flag);
     for (int a = 0; a < 5; a++) cudaFree(c->d_out[a]);
+    cudaFree(c->u2); cudaFree(c->v2); cudaFree(c->rho2);
+    for (int a = 0; a < 3; a++) cudaFree(c->out2[a]);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
@@ -445,13 +659,20 @@ static int create3d(lbm_ctx *c) {
 int lbm_create(const lbm_params *p, lbm_ctx **out) {
     if (!p || !out) return fail(LBM_ERR_INVALID, "null argument");
     *out = nullptr;
-    if (p->dim != 3) return fail(LBM_ERR_INVALID, "dim=%d not supported by this build (3 = D3Q19)", p->dim);
+    if (p->dim != 3 && p->dim != 2) return fail(LBM_ERR_INVALID, "dim=%d (3 = D3Q19 cube, 2 = D2Q9 N x M)", p->dim);
     if (p->N < 3) return fail(LBM_ERR_INVALID, "N=%d: need at least 3 grid points per side", p->N);
-    if (p->METHOD != 0 && p->METHOD != 1) return fail(LBM_ERR_INVALID, "METHOD=%d (0 = BGK, 1 = TRT)", p->METHOD);
-    if (!(p->Re > 0) || p->Re != floor(p->Re)) return fail(LBM_ERR_INVALID, "Re must be a positive integer (3D:7)");
-    if (!(p->GAMMA > 0)) return fail(LBM_ERR_INVALID, "GAMMA must be positive");
     if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks) return fail(LBM_ERR_INVALID, "bad rank/nranks");
-    if (p->nranks > p->N) return fail(LBM_ERR_INVALID, "more ranks than z planes");
+    if (p->dim == 3) {
+        if (p->METHOD != 0 && p->METHOD != 1) return fail(LBM_ERR_INVALID, "METHOD=%d (0 = BGK, 1 = TRT)", p->METHOD);
+        if (!(p->Re > 0) || p->Re != floor(p->Re)) return fail(LBM_ERR_INVALID, "Re must be a positive integer (3D:7)");
+        if (!(p->GAMMA > 0)) return fail(LBM_ERR_INVALID, "GAMMA must be positive");
+        if (p->nranks > p->N) return fail(LBM_ERR_INVALID, "more ranks than z planes");
+    } else {
+        if (p->M < 3) return fail(LBM_ERR_INVALID, "M=%d: need at least 3 rows", p->M);
+        if (p->METHOD != 1) return fail(LBM_ERR_INVALID, "dim=2 is TRT only (2D:367-413): METHOD must be 1");
+        if (!(p->Re > 0)) return fail(LBM_ERR_INVALID, "Re must be positive");
+        if (p->nranks > p->M) return fail(LBM_ERR_INVALID, "more ranks than rows");
+    }
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -503,7 +724,7 @@ int lbm_create(const lbm_params *p, lbm_ctx **out) {
         }
     }
 #undef CKD
-    rc = create3d(c);
+    rc = (p->dim == 3) ? create3d(c) : create2d(c);
     if (rc) { lbm_destroy(c); return rc; }
     *out = c;
     return LBM_OK;
@@ -514,6 +735,7 @@ int lbm_step(lbm_ctx *c, long long n) {
     if (n < 0) return fail(LBM_ERR_INVALID, "negative step count");
     if (c->unstable) return fail(LBM_ERR_UNSTABLE, "Error: negative feq.  Therefore, unstable.");
     CK(cudaSetDevice(c->dev));
+    if (c->prm.dim == 2) return step2d(c, n);
     const bool track = c->prm.track_residual != 0;
     int rc;
     if (track && n > 0) {
@@ -560,6 +782,7 @@ int lbm_step_timed(lbm_ctx *c, long long n, float *ms) {
 
 int lbm_residual(lbm_ctx *c, double *out) {
     if (!c || !out) return fail(LBM_ERR_INVALID, "null argument");
+    if (c->prm.dim == 2) { CK(cudaSetDevice(c->dev)); return residual2d(c, out); }
     if (!c->prm.track_residual) return fail(LBM_ERR_INVALID, "lbm_residual needs track_residual=1");
     if (!c->residual_ready) return fail(LBM_ERR_INVALID, "lbm_residual: no iteration since creation / lbm_set_f");
     CK(cudaSetDevice(c->dev));
@@ -583,6 +806,7 @@ int lbm_sync(lbm_ctx *c) {
 int lbm_get_f(lbm_ctx *c, double *host_full) {
     if (!c || !host_full) return fail(LBM_ERR_INVALID, "null argument");
     CK(cudaSetDevice(c->dev));
+    if (c->prm.dim == 2) return copy_dist2d(c, host_full, true);
     int rc = materialise_F(c);
     if (rc) return rc;
     const long long N3 = c->host_local ? c->FS : c->N2 * c->N;
@@ -597,6 +821,13 @@ int lbm_get_f(lbm_ctx *c, double *host_full) {
 int lbm_set_f(lbm_ctx *c, const double *host_f, const double *host_f_prev) {
     if (!c || !host_f) return fail(LBM_ERR_INVALID, "null argument");
     CK(cudaSetDevice(c->dev));
+    if (c->prm.dim == 2) {
+        if (c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
+        int rc2 = copy_dist2d(c, const_cast<double *>(host_f), false);
+        if (rc2) return rc2;
+        if (c->prm.nranks > 1) { if ((rc2 = halo_exchange2d(c, c->lat[c->cur], c->s_main))) return rc2; CK(cudaStreamSynchronize(c->s_main)); }
+        return LBM_OK;
+    }
     int rc = ensure_Fbuf(c);
     if (rc) return rc;
     if (c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
@@ -653,6 +884,7 @@ int lbm_set_f(lbm_ctx *c, const double *host_f, const double *host_f_prev) {
 int lbm_macrovars(lbm_ctx *c, double *u1, double *u2, double *u3, double *rho, double *vmag) {
     if (!c) return fail(LBM_ERR_INVALID, "null context");
     CK(cudaSetDevice(c->dev));
+    if (c->prm.dim == 2) return macrovars2d(c, u1, u2, rho, vmag);
     int rc = materialise_F(c);
     if (rc) return rc;
     double *host[5] = {u1, u2, u3, rho, vmag};
@@ -676,8 +908,8 @@ int lbm_get_info(lbm_ctx *c, lbm_info *o) {
     memset(o, 0, sizeof(*o));
     o->NU = c->NU; o->TAU = c->TAU; o->OMEGA = c->OMEGA; o->OMEGAm = c->OMEGAm; o->OmOMEGA = c->OmOMEGA;
     o->ulid = c->ulid; o->vlid = c->vlid; o->wlid = c->wlid;
-    o->Q = lbm3d::Q; o->k0 = c->k0; o->k1 = c->k1;
-    o->cells_local = c->FS; o->cells_global = c->N2 * c->N;
+    o->Q = c->prm.dim == 2 ? lbm2d::Q : lbm3d::Q; o->k0 = c->k0; o->k1 = c->k1;
+    o->cells_local = c->FS; o->cells_global = c->prm.dim == 2 ? (long long)c->N * c->M2 : c->N2 * c->N;
     o->steps_done = c->steps; o->kernel_launches = c->launches; o->device_bytes = c->bytes;
     return LBM_OK;
 }
@@ -703,7 +935,7 @@ int lbm_set_option(lbm_ctx *c, const char *key, long long value) {
     if (c->block_x > 0 && c->block_y > 0 && c->block_x * c->block_y > 256)
         return fail(LBM_ERR_INVALID, "block_x*block_y > 256");
     // partial-sum buffer depends on the block shape
-    if (c->prm.track_residual) return ensure_partials(c);
+    if (c->prm.dim == 3 && c->prm.track_residual) return ensure_partials(c);
     return LBM_OK;
 }
 

@@ -86,6 +86,49 @@ def build(cfg, force=False):
     return out
 
 
+# ---- the 2D program (D2Q9), built over oracle/mpi_shim/mpi.h ---------------------------------------
+REF_MAIN_2D = "/root/reference/2D Lid-driven Cavity with Lattice Boltzmann Method/main.cpp"
+# N, M, Re, MAXITER (iterations to run), prntInt (macroVars cadence), THRESH
+CONFIGS_2D = [
+    dict(N=100, M=300, Re="100", MAXITER="1E6", prntInt="1e3", THRESH="2E-9"),   # the reference's defaults (to convergence)
+    dict(N=24, M=40, Re="40", MAXITER="200", prntInt="1", THRESH="0"),           # 200 iterations, state after the last one
+    dict(N=17, M=23, Re="25", MAXITER="120", prntInt="1", THRESH="0"),           # odd sizes
+]
+
+
+def tag2d(c):
+    return "N{N}_M{M}_Re{Re}_it{MAXITER}_p{prntInt}_th{THRESH}".format(**c)
+
+
+def binary_path_2d(c):
+    return os.path.join(OUT, "lbm2d_ref_" + tag2d(c))
+
+
+def build2d(cfg, force=False):
+    out = binary_path_2d(cfg)
+    shim = os.path.join(HERE, "mpi_shim")
+    if (not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(os.path.join(shim, "mpi.h"))
+            and os.path.getmtime(out) >= os.path.getmtime(__file__)):
+        return out
+    os.makedirs(OUT, exist_ok=True)
+    with open(REF_MAIN_2D) as f:
+        src = f.read()
+    subs = [(r"(const double Re = )[^;]+", cfg["Re"]), (r"(const int N = )[^;]+", str(cfg["N"])),
+            (r"(const int M = )[^;]+", str(cfg["M"])), (r"(const double THRESH = )[^;]+", cfg["THRESH"]),
+            (r"(const double MAXITER = )[^;]+", cfg["MAXITER"]), (r"(const int prntInt = )[^;]+", cfg["prntInt"])]
+    for pat, val in subs:
+        src, n = re.subn(pat, lambda m: m.group(1) + val, src, count=1)
+        if n != 1:
+            raise RuntimeError("could not patch %s" % pat)
+    with tempfile.TemporaryDirectory() as tmp:
+        psrc = os.path.join(tmp, "ref2d_patched.cpp")
+        with open(psrc, "w") as f:
+            f.write(src)
+        # <mpi.h> resolves to the shim; flags as the reference CI's g++ line + -ffp-contract=off
+        subprocess.check_call(["g++", "-O3", "-ffp-contract=off", "-w", "-I", shim, psrc, "-o", out])
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--list", action="store_true")
@@ -94,12 +137,16 @@ def main():
     if a.list:
         for c in CONFIGS:
             print(binary_path(c))
+        for c in CONFIGS_2D:
+            print(binary_path_2d(c))
         return 0
     if not os.path.exists(REF_MAIN):
         print("reference not present (%s); keeping prebuilt oracle/_ref" % REF_MAIN)
         return 0
     for c in CONFIGS:
         print("built", build(c, a.force))
+    for c in CONFIGS_2D:
+        print("built", build2d(c, a.force))
     return 0
 
 

@@ -150,3 +150,90 @@ def ref_time(n, threads=0, **cfg):
     exe = ref_binary(**cfg)
     r = subprocess.run([exe, "time", str(n), str(threads)], capture_output=True, text=True, check=True)
     return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+# ---- D2Q9 (2D main.cpp) ---------------------------------------------------------------------------
+
+class Params2D(C.Structure):
+    _fields_ = [("N", C.c_int), ("M", C.c_int), ("Re", C.c_double), ("Ulid", C.c_double), ("MAGIC", C.c_double)]
+
+
+def _lib2d():
+    L = lib()
+    if not getattr(L, "_has2d", False):
+        dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+        for pre in ("oracle2d", "inplace2d"):
+            getattr(L, pre + "_create").restype = C.c_void_p
+            getattr(L, pre + "_destroy").argtypes = [C.c_void_p]
+            getattr(L, pre + "_step").argtypes = [C.c_void_p, C.c_int]
+            getattr(L, pre + "_residual").restype = C.c_double
+            getattr(L, pre + "_residual").argtypes = [C.c_void_p]
+            getattr(L, pre + "_get_macro").argtypes = [C.c_void_p, dp, dp, dp]
+        L.oracle2d_create.argtypes = [C.POINTER(Params2D)]
+        L.inplace2d_create.argtypes = [C.POINTER(Params2D), C.c_int]
+        L.oracle2d_get_dist.argtypes = [C.c_void_p, dp]
+        L.oracle2d_derived.argtypes = [C.POINTER(Params2D), dp]
+        L._has2d = True
+    return L
+
+
+class Oracle2D:
+    """D2Q9 cavity.  scheme='sync': two-lattice synchronous update (what the GPU computes);
+    scheme='inplace': literal emulation of the reference's in-place sweep with `ranks` MPI ranks."""
+
+    def __init__(self, N=100, M=300, Re=100.0, Ulid=0.1, MAGIC=0.25, scheme="sync", ranks=3):
+        self.N, self.M, self.scheme = N, M, scheme
+        self.p = Params2D(N=N, M=M, Re=Re, Ulid=Ulid, MAGIC=MAGIC)
+        L = _lib2d()
+        self.pre = "oracle2d" if scheme == "sync" else "inplace2d"
+        self.h = L.oracle2d_create(C.byref(self.p)) if scheme == "sync" else L.inplace2d_create(C.byref(self.p), ranks)
+
+    def step(self, n=1):
+        getattr(_lib2d(), self.pre + "_step")(self.h, n)
+
+    def residual(self):
+        return getattr(_lib2d(), self.pre + "_residual")(self.h)
+
+    def macro(self):
+        a = [np.empty(self.N * self.M) for _ in range(3)]
+        getattr(_lib2d(), self.pre + "_get_macro")(self.h, *a)
+        return dict(u=a[0], v=a[1], rho=a[2])
+
+    def dist(self):
+        assert self.scheme == "sync"
+        out = np.empty(9 * self.N * self.M)
+        _lib2d().oracle2d_get_dist(self.h, out)
+        return out
+
+    def derived(self):
+        out = np.empty(4)
+        _lib2d().oracle2d_derived(C.byref(self.p), out)
+        return dict(zip(["NU", "TAU", "OMEGA", "OMEGAm"], out.tolist()))
+
+    def close(self):
+        if self.h:
+            getattr(_lib2d(), self.pre + "_destroy")(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ref2d_binary(N, M, Re, MAXITER, prntInt, THRESH):
+    return os.path.join(REF_DIR, "lbm2d_ref_N{}_M{}_Re{}_it{}_p{}_th{}".format(N, M, Re, MAXITER, prntInt, THRESH))
+
+
+def ref2d_run(ranks, **cfg):
+    """Run the REAL 2D reference (built over oracle/mpi_shim) with `ranks` ranks in a temp dir;
+    returns (dict of u, v, rho, x, y arrays [M*N], stdout)."""
+    exe = ref2d_binary(**cfg)
+    with tempfile.TemporaryDirectory() as tmp:
+        env = dict(os.environ, SHIM_NP=str(ranks))
+        r = subprocess.run([exe], capture_output=True, text=True, cwd=tmp, env=env, check=True)
+        out = {}
+        for name in ("u", "v", "rho", "x", "y"):
+            out[name] = np.fromfile(os.path.join(tmp, "Re=%.0f_N=%d_M=%d_%s.bin" % (float(cfg["Re"]), cfg["N"], cfg["M"], name)))
+        return out, r.stdout

@@ -363,7 +363,7 @@ static lbm2d::KP2 make_kp2(const lbm_ctx *c, const double *src, double *dst) {
 static int block2d(const lbm_ctx *c) {
     if (c->block_x > 0) return c->block_x;
     int bx = ((c->N + 31) / 32) * 32;
-    if (bx > 128) bx = 128;
+    if (bx > 256) bx = 256;  // 256 measured best at 8192^2 (profiles/r01_sweep2d.log)
     return bx;
 }
 

@@ -1,0 +1,59 @@
+"""GPU tests of the C host programs (cfd-codes_b200/host/main.c, main2d.c): the drop-in
+replacements of the reference's two executables, driven exactly as a user would."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+EXE3 = os.path.join(ROOT, "cfd-codes_b200", "lbm3d_cavity")
+EXE2 = os.path.join(ROOT, "cfd-codes_b200", "lbm2d_cavity")
+
+
+def test_lbm3d_cavity_reproduces_the_golden_run(tmp_path):
+    """`lbm3d_cavity --N 29` = the reference built with N 29: same stdout blocks (SURVEY App. C:
+    'Iteration 0: df 1.909e+00', converges at 'Iteration 43500: df/df0 8.340e-13') and the same
+    Solution_*.dat as the reference's shipped example output (numeric compare; zero signs aside)."""
+    r = subprocess.run([EXE3, "--N", "29"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    out = r.stdout
+    assert out.startswith("Threads used:\t1\nRe =\t100\nRe_g =\t")
+    assert "N =\t29\n" in out and "tau =\t5.900e-01\n" in out and "nu =\t3.000e-02\n" in out and "M =\t1.732e-01\n" in out
+    assert "\nIteration 0:\ndf:\t1.909e+00\n" in out
+    its = re.findall(r"\nIteration (\d+):\ndf/df0:\t(\S+)\nTime:\t\S+ s\nLUPS:\t\S+ s\n", out)
+    assert its[0][0] == "500" and its[-1] == ("43500", "8.340e-13") and len(its) == 87
+    path = tmp_path / "Solution_n=29Re=100_DIAG=0_2RT_M=0.250.dat"
+    g = np.load(os.path.join(GOLD, "solution_n29_re100.npz"))
+    with open(path) as fh:
+        header = fh.readline().rstrip("\n")
+        data = np.loadtxt(fh, delimiter=",")
+    assert header == str(g["header"])
+    assert data.shape == (29 ** 3, 7)
+    for col, name in enumerate(("x", "y", "z", "u", "v", "w", "vmag")):
+        assert np.array_equal(data[:, col] + 0.0, g[name] + 0.0), name   # identical at the 10 printed decimals
+
+
+def test_lbm3d_cavity_reports_instability_like_the_reference(tmp_path):
+    r = subprocess.run([EXE3, "--N", "12", "--METHOD", "0", "--SAVETXT", "0"], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 1
+    assert r.stdout.rstrip().endswith("Error: negative feq.  Therefore, unstable.")
+
+
+def test_lbm2d_cavity_outputs(tmp_path):
+    r = subprocess.run([EXE2, "--N", "40", "--M", "60", "--Re", "50", "--THRESH", "1e-6"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    out = r.stdout
+    assert out.startswith("MPI LBM Simulation of Lid Driven Cavity\nDomain Size: 40 x 60\nRe\t= 50\nnu\t= 0.08\ntau\t= 0.74\nUmax\t= 0.1\n")
+    assert "Rank 0: 60 nodes from y =   0 to y =  59 (BOTTOM)" in out
+    rows = re.findall(r"^(\d\.\d{3}e[+-]\d+)\t(\d\.\d{3}e[+-]\d+)\t", out, flags=re.M)
+    assert rows[0][0] == "0.000e+00" and rows[0][1] == "1.000e+00" and float(rows[-1][1]) < 1e-6
+    u = np.fromfile(tmp_path / "Re=50_N=40_M=60_u.bin").reshape(60, 40)
+    x = np.fromfile(tmp_path / "Re=50_N=40_M=60_x.bin").reshape(60, 40)
+    rho = np.fromfile(tmp_path / "Re=50_N=40_M=60_rho.bin")
+    assert np.array_equal(x[0], 0.5 + np.arange(40)) and u[59].min() > 0.0 and u[59].mean() > 0.05 and abs(rho.mean() - 1.0) < 1e-3

@@ -70,6 +70,32 @@ struct KP {
     double ulid, vlid, wlid, vfrac, third, sixth;  // 3D:183-191, 386, 41-42
 };
 
+// ---- global memory access policy (tuned with tools/ab_variants.sh; default = plain LDG/STG) ------
+__device__ __forceinline__ double lbm_load(const double *p) {
+#if defined(LBM_LD_NA)
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+#elif defined(LBM_LD_CS)
+    return __ldcs(p);
+#elif defined(LBM_LD_CG)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+__device__ __forceinline__ void lbm_store(double *p, double v) {
+#if defined(LBM_ST_CS)
+    __stcs(p, v);
+#elif defined(LBM_ST_CG)
+    __stcg(p, v);
+#elif defined(LBM_ST_WT)
+    __stwt(p, v);
+#else
+    *p = v;
+#endif
+}
+
 // ---- collision --------------------------------------------------------------------------------
 // In place: f (pre-collision, the reference's f1[x][:]) -> post-collision f*.  Returns true if any
 // equilibrium was negative (checkfeq, 3D:687-692).
@@ -82,7 +108,8 @@ struct KP {
 //   OMEGA*(0.5*(a+b) - 0.5*(c+d)) == (0.5*OMEGA)*((a+b) - (c+d))   bit for bit (3D:293-299).
 // checkfeq (feq < 0.0, 3D:688) is evaluated on the sign bits: the OR of the high words is
 // negative iff some feq has its sign bit set (feq = -0.0 cannot occur for finite rho != 0).
-template <int METHOD>
+// G1: GAMMA == 1.0 (the reference default): x * gammainv == x exactly, so the multiply is dropped.
+template <int METHOD, bool G1>
 __device__ __forceinline__ bool collide(double (&f)[Q], const KP &p) {
     // 3D:268-270 / 3D:225-235 (the += loop visits q = 0..18: same order, zero terms are exact)
     double rho = f[0] + f[1];
@@ -112,7 +139,7 @@ __device__ __forceinline__ bool collide(double (&f)[Q], const KP &p) {
     const double homega = 0.5 * p.omega, homegam = 0.5 * p.omegam;  // exact
 
     {   // rest population, cdotu = 0: feq = w*rho*(1.0 + (0 - 1.5*U2)*gammainv)
-        const double fe = wr0 * (1.0 + (-k15) * p.gammainv);
+        const double fe = wr0 * (1.0 + (G1 ? (-k15) : (-k15) * p.gammainv));
         negbits |= __double2hiint(fe);
         if (METHOD == 1) f[0] = f[0] - p.omega * (f[0] - fe);        // 3D:286
         else             f[0] = p.omomega * f[0] + p.omega * fe;     // 3D:246
@@ -120,7 +147,7 @@ __device__ __forceinline__ bool collide(double (&f)[Q], const KP &p) {
 #define LBM_PAIR(q, c, cc, wr)                                                                       \
     {                                                                                                \
         const double t3 = 3.0 * (c);                                                                 \
-        const double E = (4.5 * (cc) - k15) * p.gammainv;                                            \
+        const double E = G1 ? (4.5 * (cc) - k15) : (4.5 * (cc) - k15) * p.gammainv;                  \
         const double fe1 = (wr) * ((1.0 + t3) + E);                                                  \
         const double fe2 = (wr) * ((1.0 - t3) + E);                                                  \
         negbits |= __double2hiint(fe1) | __double2hiint(fe2);                                        \
@@ -232,7 +259,7 @@ __device__ __forceinline__ double block_sum(double v) {
 
 // ---- the fused step kernel ------------------------------------------------------------------------
 // grid = (ceil(N/bx), ceil(N/by), planes of this launch); block = (bx, by), bx*by <= 256.
-template <int METHOD, int MODE>
+template <int METHOD, int MODE, bool G1>
 __global__ void __launch_bounds__(256, 2) k_step(const __grid_constant__ KP p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -252,7 +279,7 @@ __global__ void __launch_bounds__(256, 2) k_step(const __grid_constant__ KP p) {
 
         double f[Q];
         // 1. pull: unconditional, coalesced 8-byte loads through the pre-shifted bases.
-#define LBM_PULL(q, cx, cy, cz, wq) f[q] = p.srcq[q][cell];
+#define LBM_PULL(q, cx, cy, cz, wq) f[q] = lbm_load(p.srcq[q] + cell);
         LBM_D3Q19_VEL(LBM_PULL)
 #undef LBM_PULL
 
@@ -293,10 +320,10 @@ __global__ void __launch_bounds__(256, 2) k_step(const __grid_constant__ KP p) {
 
         // 3. collide + store
         if (MODE != MODE_MATERIALISE) {
-            const bool neg = collide<METHOD>(f, p);
+            const bool neg = collide<METHOD, G1>(f, p);
             if (neg) atomicOr(p.flag, 1);
 #pragma unroll
-            for (int q = 0; q < Q; q++) p.dstq[q][cell] = f[q];
+            for (int q = 0; q < Q; q++) lbm_store(p.dstq[q] + cell, f[q]);
         }
     }
 
@@ -329,7 +356,7 @@ __global__ void __launch_bounds__(256, 2) k_collide_cells(const __grid_constant_
         LBM_D3Q19_VEL(LBM_SETW)
 #undef LBM_SETW
     }
-    const bool neg = collide<METHOD>(f, p);
+    const bool neg = collide<METHOD, false>(f, p);
     if (neg) atomicOr(p.flag, 1);
     const int cell = (kl + 1) * (int)p.N2 + (int)rowcell;
 #pragma unroll

@@ -12,6 +12,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/lbm_b200.h"
 #include "lbm3d_kernels.cuh"
 #include "lbm2d_kernels.cuh"
@@ -120,6 +122,13 @@ struct lbm_ctx {
     double lid6 = 0.0;
 
     long long steps = 0, launches = 0, bytes = 0;
+    // device time of the plain step iterations (the dominant kernel), measured with CUDA events
+    // around each batch of consecutive MODE_STEP iterations inside lbm_step; resolved lazily
+    struct Span { cudaEvent_t a, b; long long iters; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> ev_pool;
+    double plain_ms = 0.0;
+    long long plain_iters = 0;
     int block_x = 0, block_y = 0;
     bool host_local = false;  // host arrays are compact local slabs instead of full LU4/LU3 arrays
     ncclComm_t comm = nullptr;
@@ -190,8 +199,14 @@ static lbm3d::KP make_kp(const lbm_ctx *c) {
 
 template <int MODE>
 static void launch_step_mode(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, dim3 blk) {
-    if (c->prm.METHOD == 1) lbm3d::k_step<1, MODE><<<grid, blk, 0, c->s_main>>>(p);
-    else                    lbm3d::k_step<0, MODE><<<grid, blk, 0, c->s_main>>>(p);
+    const bool g1 = (c->prm.GAMMA == 1.0);  // x * (1.0 / 1.0) == x: the specialised kernel drops the multiply
+    if (c->prm.METHOD == 1) {
+        if (g1) lbm3d::k_step<1, MODE, true><<<grid, blk, 0, c->s_main>>>(p);
+        else    lbm3d::k_step<1, MODE, false><<<grid, blk, 0, c->s_main>>>(p);
+    } else {
+        if (g1) lbm3d::k_step<0, MODE, true><<<grid, blk, 0, c->s_main>>>(p);
+        else    lbm3d::k_step<0, MODE, false><<<grid, blk, 0, c->s_main>>>(p);
+    }
     c->launches++;
 }
 
@@ -536,6 +551,32 @@ static int macrovars2d(lbm_ctx *c, double *u, double *v, double *rho, double *vm
     return LBM_OK;
 }
 
+static cudaEvent_t span_event(lbm_ctx *c) {
+    if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// Fold finished spans into plain_ms / plain_iters (wait == true: synchronise on the open ones too).
+static void resolve_spans(lbm_ctx *c, bool wait) {
+    size_t keep = 0;
+    for (size_t k = 0; k < c->spans.size(); k++) {
+        lbm_ctx::Span &sp = c->spans[k];
+        cudaError_t e = wait ? cudaEventSynchronize(sp.b) : cudaEventQuery(sp.b);
+        if (e == cudaSuccess) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { c->plain_ms += ms; c->plain_iters += sp.iters; }
+            c->ev_pool.push_back(sp.a);
+            c->ev_pool.push_back(sp.b);
+        } else {
+            c->spans[keep++] = sp;
+        }
+    }
+    c->spans.resize(keep);
+    cudaGetLastError();  // cudaErrorNotReady from the queries is not an error
+}
+
 // ---- C ABI ---------------------------------------------------------------------------------------
 extern "C" {
 
@@ -576,6 +617,8 @@ int lbm_destroy(lbm_ctx *c) {
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->s_halo) cudaStreamDestroy(c->s_halo);
     if (c->own_main && c->s_main) cudaStreamDestroy(c->s_main);
     delete c;
@@ -743,6 +786,15 @@ int lbm_step(lbm_ctx *c, long long n) {
         if ((rc = ensure_partials(c))) return rc;
         if (n == 1 && !c->f_valid) { if ((rc = materialise_F(c))) return rc; }
     }
+    const long long n_plain = track ? n - 2 : n;  // the leading iterations run the plain step kernel
+    lbm_ctx::Span sp{nullptr, nullptr, 0};
+    if (n_plain > 0) {
+        if (c->spans.size() > 256) resolve_spans(c, false);
+        sp.a = span_event(c);
+        sp.b = span_event(c);
+        sp.iters = n_plain;
+        CK(cudaEventRecord(sp.a, c->s_main));
+    }
     for (long long t = 0; t < n; t++) {
         int mode = lbm3d::MODE_STEP;
         if (track) {
@@ -750,6 +802,10 @@ int lbm_step(lbm_ctx *c, long long n) {
             else if (t == n - 2) mode = lbm3d::MODE_STEP_STOREF;     // leaves F(t-1) for the last iteration
         }
         if ((rc = run_iteration(c, mode))) return rc;
+        if (t == n_plain - 1) {
+            CK(cudaEventRecord(sp.b, c->s_main));
+            c->spans.push_back(sp);
+        }
     }
     return LBM_OK;
 }
@@ -911,6 +967,9 @@ int lbm_get_info(lbm_ctx *c, lbm_info *o) {
     o->Q = c->prm.dim == 2 ? lbm2d::Q : lbm3d::Q; o->k0 = c->k0; o->k1 = c->k1;
     o->cells_local = c->FS; o->cells_global = c->prm.dim == 2 ? (long long)c->N * c->M2 : c->N2 * c->N;
     o->steps_done = c->steps; o->kernel_launches = c->launches; o->device_bytes = c->bytes;
+    cudaSetDevice(c->dev);
+    resolve_spans(c, true);
+    o->plain_step_ms = c->plain_ms; o->plain_step_iterations = c->plain_iters;
     return LBM_OK;
 }
 

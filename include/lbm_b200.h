@@ -69,6 +69,9 @@ typedef struct lbm_info {
     long long steps_done;         /* iterations executed since creation / lbm_set_f */
     long long kernel_launches;    /* kernels launched by this context so far */
     long long device_bytes;       /* device memory currently allocated by this context */
+    double plain_step_ms;         /* accumulated device time (CUDA events on the launching stream) of the
+                                     iterations run by the plain step kernel inside lbm_step (dim=3) ... */
+    long long plain_step_iterations; /* ... and how many iterations that covers */
 } lbm_info;
 
 /* Fills *p with the reference's defaults: dim=3, N=50, Re=100, UMAX=0.1, METHOD=1 (TRT), GAMMA=1,

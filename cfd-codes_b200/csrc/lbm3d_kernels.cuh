@@ -258,9 +258,17 @@ __device__ __forceinline__ double block_sum(double v) {
 }
 
 // ---- the fused step kernel ------------------------------------------------------------------------
-// grid = (ceil(N/bx), ceil(N/by), planes of this launch); block = (bx, by), bx*by <= 256.
+// grid = (ceil(N/bx), ceil(N/by), planes of this launch); block = (bx, by), bx*by <= 128.
+// Launch bounds tuned on B200 (profiles/r01_ab_occupancy.log): 128-thread blocks, >= 5 resident
+// blocks per SM (<= 102 registers; ptxas uses 94 without spilling) -> 20 warps/SM.  With the looser
+// bound (122 registers, 16 warps/SM) the kernel matches the copy bandwidth only at boost clocks and
+// loses 2.5 % once the 1000 W power cap pulls the SM clock to ~1.6 GHz; a tighter bound spills.
+#ifndef LBM_STEP_MAX_THREADS
+#define LBM_STEP_MAX_THREADS 128
+#define LBM_STEP_MIN_BLOCKS 5
+#endif
 template <int METHOD, int MODE, bool G1>
-__global__ void __launch_bounds__(256, 2) k_step(const __grid_constant__ KP p) {
+__global__ void __launch_bounds__(LBM_STEP_MAX_THREADS, LBM_STEP_MIN_BLOCKS) k_step(const __grid_constant__ KP p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int kl = p.kl0 + blockIdx.z * p.kstride;
@@ -340,7 +348,7 @@ __global__ void __launch_bounds__(256, 2) k_step(const __grid_constant__ KP p) {
 // F = w (initial state, 3D:192-205: feq(rho=1,u=0) = w[q] exactly) when Fbuf == nullptr.
 // Covers ghost planes too when `with_ghosts` (initial state only: uniform).
 template <int METHOD>
-__global__ void __launch_bounds__(256, 2) k_collide_cells(const __grid_constant__ KP p, const int with_ghosts) {
+__global__ void __launch_bounds__(128, 4) k_collide_cells(const __grid_constant__ KP p, const int with_ghosts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int kl = (int)blockIdx.z - (with_ghosts ? 1 : 0);

@@ -976,7 +976,8 @@ int lbm_get_info(lbm_ctx *c, lbm_info *o) {
 int lbm_set_option(lbm_ctx *c, const char *key, long long value) {
     if (!c || !key) return fail(LBM_ERR_INVALID, "null argument");
     if (!strcmp(key, "block_x")) {
-        if (value < 0 || value > 256 || (value % 32)) return fail(LBM_ERR_INVALID, "block_x must be a multiple of 32 <= 256");
+        const int lim = c->prm.dim == 2 ? 256 : 128;
+        if (value < 0 || value > lim || (value % 32)) return fail(LBM_ERR_INVALID, "block_x must be a multiple of 32 <= %d", lim);
         c->block_x = (int)value;
     } else if (!strcmp(key, "block_y")) {
         if (value < 0 || value > 256) return fail(LBM_ERR_INVALID, "block_y out of range");
@@ -991,8 +992,8 @@ int lbm_set_option(lbm_ctx *c, const char *key, long long value) {
     } else {
         return fail(LBM_ERR_INVALID, "unknown option %s", key);
     }
-    if (c->block_x > 0 && c->block_y > 0 && c->block_x * c->block_y > 256)
-        return fail(LBM_ERR_INVALID, "block_x*block_y > 256");
+    if (c->prm.dim == 3 && c->block_x > 0 && c->block_y > 0 && c->block_x * c->block_y > 128)
+        return fail(LBM_ERR_INVALID, "block_x*block_y > 128");
     // partial-sum buffer depends on the block shape
     if (c->prm.dim == 3 && c->prm.track_residual) return ensure_partials(c);
     return LBM_OK;

@@ -88,7 +88,7 @@ def test_step_splitting_and_untracked_mode_do_not_change_the_field(lbm):
 def test_block_shape_does_not_change_the_field(lbm):
     cfg = dict(N=40, Re=100)
     ref = None
-    for bx, by in ((0, 0), (32, 8), (64, 1), (64, 4), (128, 2)):
+    for bx, by in ((0, 0), (32, 4), (64, 1), (64, 2), (128, 1), (96, 1)):
         with lbm.Cavity3D(**cfg) as sim:
             if bx:
                 sim.set_option("block_x", bx)
@@ -189,7 +189,7 @@ def test_size_independent_properties_at_512(lbm):
         u = mv["u1"].reshape(N, N, N)
         assert u[N // 2, N - 2, N // 2] > 0 and u[N // 2, N // 2, N // 2] == 0.0
     with lbm.Cavity3D(N=N, Re=1000, track_residual=False) as sim:
-        sim.set_option("block_x", 128)
+        sim.set_option("block_x", 64)
         sim.set_option("block_y", 2)
         for n in (1, 2, 3):
             sim.step(n)

@@ -11,7 +11,7 @@ from lbmpkg import lbm  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--grids", default="256,512")
-ap.add_argument("--blocks", default="0x0,256x1,128x2,128x1,64x4,64x2,32x8")
+ap.add_argument("--blocks", default="0x0,128x1,64x2,64x1,32x4,96x1")
 ap.add_argument("--iters", type=int, default=200)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--method", type=int, default=1)

@@ -44,6 +44,10 @@ CONFIGS = [
     dict(N=50, Re=100),                      # reference defaults (config 1)
     dict(N=64, Re=253),                      # same tau as 256^3/Re=1000
     dict(N=256, Re=1000),                    # bench config 2 (CPU baseline, kind "reference")
+    dict(N=3, Re=10),                        # smallest legal grid: one fluid cell, every rule class has one cell
+    dict(N=4, Re=10, METHOD=0),              # no face-interior ... 2x2 faces, BGK
+    dict(N=5, Re=30, DIAG=1, GAMMA="2.0", UMAX="0.05"),   # GAMMA > 1, other lid speed
+    dict(N=16, Re=200, UMAX="0.2", GAMMA="0.8"),
 ]
 
 

@@ -37,6 +37,10 @@ HASH_CASES = [
     (dict(N=32, Re=65, METHOD=0), [100]),
     (dict(N=50, Re=100), [20, 501]),
     (dict(N=64, Re=253), [30]),
+    (dict(N=3, Re=10), [1, 2, 3, 50]),
+    (dict(N=4, Re=10, METHOD=0), [1, 2, 3, 50]),
+    (dict(N=5, Re=30, DIAG=1, GAMMA="2.0", UMAX="0.05"), [1, 2, 3, 80]),
+    (dict(N=16, Re=200, UMAX="0.2", GAMMA="0.8"), [1, 5, 120]),
 ]
 
 

@@ -344,6 +344,67 @@ __global__ void __launch_bounds__(LBM_STEP_MAX_THREADS, LBM_STEP_MIN_BLOCKS) k_s
     }
 }
 
+// ---- 128-bit variant of the plain step: two x-adjacent cells per thread --------------------------
+// (north_star item 2.)  Needs N even.  The 9 populations with cx = 0 are pulled with one aligned
+// 16-byte load per pair of cells, the 10 x-shifted ones with two 8-byte loads (their pair straddles
+// a 16-byte boundary); all 19 are stored with aligned 16-byte stores.  Same arithmetic, same bits.
+#ifndef LBM_STEP2_MIN_BLOCKS
+#define LBM_STEP2_MIN_BLOCKS 3
+#endif
+template <int METHOD, bool G1>
+__global__ void __launch_bounds__(128, LBM_STEP2_MIN_BLOCKS) k_step_x2(const __grid_constant__ KP p) {
+    const int i0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int kl = p.kl0 + blockIdx.z * p.kstride;
+    if (i0 >= p.N || j >= p.N) return;
+    const int kg = kl + p.k0;
+    const int by = (j == 0) ? 1 : ((j == p.M) ? 2 : 0);
+    const int bz = (kg == 0) ? 1 : ((kg == p.Mz) ? 2 : 0);
+    const int bxa = (i0 == 0) ? 1 : 0;                 // cell a = (i0, j, k): can only touch x = 0
+    const int bxb = (i0 + 1 == p.M) ? 2 : 0;           // cell b = (i0+1, j, k): can only touch x = N-1
+    const int clsa = LBM_CLS(bxa, by, bz), clsb = LBM_CLS(bxb, by, bz);
+    const int N1 = p.N;
+    const int cell = (kl + 1) * (int)p.N2 + j * N1 + i0;
+
+    double fa[Q], fb[Q];
+#define LBM_PULL2(q, cx, cy, cz, wq)                                                                 \
+    if (cx == 0) {                                                                                   \
+        const double2 v = *reinterpret_cast<const double2 *>(p.srcq[q] + cell);                      \
+        fa[q] = v.x; fb[q] = v.y;                                                                    \
+    } else {                                                                                         \
+        fa[q] = p.srcq[q][cell]; fb[q] = p.srcq[q][cell + 1];                                        \
+    }
+    LBM_D3Q19_VEL(LBM_PULL2)
+#undef LBM_PULL2
+
+#define LBM_FIXA(q, cx, cy, cz, wq)                                                                  \
+    if ((cx == 1 && bxa == 1) || (cy == 1 && by == 1) || (cy == -1 && by == 2) || (cz == 1 && bz == 1) || \
+        (cz == -1 && bz == 2))                                                                       \
+        fa[q] = (wq);
+#define LBM_FIXB(q, cx, cy, cz, wq)                                                                  \
+    if ((cx == -1 && bxb == 2) || (cy == 1 && by == 1) || (cy == -1 && by == 2) || (cz == 1 && bz == 1) || \
+        (cz == -1 && bz == 2))                                                                       \
+        fb[q] = (wq);
+    if (clsa != 0) {
+        LBM_D3Q19_VEL(LBM_FIXA)
+        apply_boundary(fa, clsa, p);
+    }
+    if (clsb != 0) {
+        LBM_D3Q19_VEL(LBM_FIXB)
+        const bool xm_face = (clsb == LBM_CLS(2, 0, 0));
+        if (xm_face) fb[14] = p.side_rd[kl * N1 + j];   // stale f14, see k_step
+        apply_boundary(fb, clsb, p);
+        if (xm_face) p.side_wr[kl * N1 + j] = fb[14];
+    }
+#undef LBM_FIXA
+#undef LBM_FIXB
+    const bool nega = collide<METHOD, G1>(fa, p);
+    const bool negb = collide<METHOD, G1>(fb, p);
+    if (nega | negb) atomicOr(p.flag, 1);
+#pragma unroll
+    for (int q = 0; q < Q; q++) *reinterpret_cast<double2 *>(p.dstq[q] + cell) = make_double2(fa[q], fb[q]);
+}
+
 // S = collide(F) for every owned cell, F taken from the F buffer (restart, lbm_set_f), or
 // F = w (initial state, 3D:192-205: feq(rho=1,u=0) = w[q] exactly) when Fbuf == nullptr.
 // Covers ghost planes too when `with_ghosts` (initial state only: uniform).

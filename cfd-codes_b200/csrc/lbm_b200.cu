@@ -130,6 +130,7 @@ struct lbm_ctx {
     double plain_ms = 0.0;
     long long plain_iters = 0;
     int block_x = 0, block_y = 0;
+    int vec2 = 0;  // 1: plain iterations use the two-cells-per-thread 128-bit kernel (N even)
     bool host_local = false;  // host arrays are compact local slabs instead of full LU4/LU3 arrays
     ncclComm_t comm = nullptr;
 };
@@ -211,6 +212,19 @@ static void launch_step_mode(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, dim3 blk
 }
 
 static void launch_step(lbm_ctx *c, int mode, const lbm3d::KP &p, dim3 grid, dim3 blk) {
+    if (mode == lbm3d::MODE_STEP && c->vec2 && (c->N % 2) == 0) {
+        const bool g1 = (c->prm.GAMMA == 1.0);
+        dim3 g2((c->N / 2 + blk.x - 1) / blk.x, grid.y, grid.z);
+        if (c->prm.METHOD == 1) {
+            if (g1) lbm3d::k_step_x2<1, true><<<g2, blk, 0, c->s_main>>>(p);
+            else    lbm3d::k_step_x2<1, false><<<g2, blk, 0, c->s_main>>>(p);
+        } else {
+            if (g1) lbm3d::k_step_x2<0, true><<<g2, blk, 0, c->s_main>>>(p);
+            else    lbm3d::k_step_x2<0, false><<<g2, blk, 0, c->s_main>>>(p);
+        }
+        c->launches++;
+        return;
+    }
     switch (mode) {
         case lbm3d::MODE_STEP: launch_step_mode<lbm3d::MODE_STEP>(c, p, grid, blk); break;
         case lbm3d::MODE_STEP_STOREF: launch_step_mode<lbm3d::MODE_STEP_STOREF>(c, p, grid, blk); break;
@@ -982,6 +996,9 @@ int lbm_set_option(lbm_ctx *c, const char *key, long long value) {
     } else if (!strcmp(key, "block_y")) {
         if (value < 0 || value > 256) return fail(LBM_ERR_INVALID, "block_y out of range");
         c->block_y = (int)value;
+    } else if (!strcmp(key, "vec2")) {
+        c->vec2 = value != 0;
+        return LBM_OK;
     } else if (!strcmp(key, "host_local_layout")) {
         c->host_local = value != 0;
         return LBM_OK;

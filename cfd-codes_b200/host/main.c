@@ -26,6 +26,11 @@
 #include <string.h>
 #include <time.h>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "fmt10.h"
 #include "lbm_b200.h"
 
 typedef struct {
@@ -58,7 +63,9 @@ static void die_lbm(int rc) {
     exit(1);
 }
 
-/* Writes the Tecplot file, 3D:363-382: i outer, j, k inner; x = y = z = linspace(0, N-1, N) (3D:175). */
+/* Writes the Tecplot file, 3D:363-382: i outer, j, k inner; x = y = z = linspace(0, N-1, N) (3D:175).
+ * Same bytes as the reference's fprintf("%.10f, ...") loop, produced by an exact integer formatter
+ * (fmt10.h) on all host threads: one i-slice (N^2 lines) per thread, written in order. */
 static void datwrite(const options *o, const double *u1, const double *u2, const double *u3, const double *vmag) {
     char filename[160];
     snprintf(filename, sizeof filename, "Solution_n=%dRe=%d_DIAG=%d_%dRT_M=%.3f.dat", o->N, o->Re, o->DIAG,
@@ -72,14 +79,41 @@ static void datwrite(const options *o, const double *u1, const double *u2, const
     const size_t N1 = (size_t)N, N2 = N1 * N1;
     fprintf(fp, "TITLE=\"%s\" VARIABLES=\"x\", \"y\", \"z\", \"%s\", \"%s\", \"%s\", \"vmag\" ZONE T=\"%s\" I=%d J=%d K=%d F=POINT\n",
             filename, "u", "v", "w", filename, N, N, N);
-    for (int i = 0; i < N; i++)
-        for (int j = 0; j < N; j++)
-            for (int k = 0; k < N; k++) {
-                const size_t c = (size_t)k * N2 + (size_t)j * N1 + (size_t)i; /* LU3, 3D:47 */
-                /* linspace(0, N-1, N): start + i*(stop-start)/(num-1) is exactly i (3D:328) */
-                fprintf(fp, "%.10f, %.10f, %.10f, %.10f, %.10f, %.10f, %.10f\n", (double)i, (double)j, (double)k,
-                        u1[c], u2[c], u3[c], vmag[c]);
-            }
+    int T = 1;
+#ifdef _OPENMP
+    T = omp_get_max_threads();
+#endif
+    if (T > N) T = N;
+    const size_t line_max = 7 * 24 + 16;
+    char **bufs = malloc((size_t)T * sizeof(char *));
+    size_t *lens = calloc((size_t)T, sizeof(size_t));
+    for (int t = 0; t < T; t++) {
+        bufs[t] = malloc(N2 * line_max);
+        if (!bufs[t]) { printf("Error allocating memory!\n"); exit(1); }
+    }
+    for (int i0 = 0; i0 < N; i0 += T) {
+        const int i1 = i0 + T < N ? i0 + T : N;
+#pragma omp parallel for schedule(static, 1)
+        for (int i = i0; i < i1; i++) {
+            char *p = bufs[i - i0];
+            for (int j = 0; j < N; j++)
+                for (int k = 0; k < N; k++) {
+                    const size_t c = (size_t)k * N2 + (size_t)j * N1 + (size_t)i; /* LU3, 3D:47 */
+                    /* linspace(0, N-1, N): start + i*(stop-start)/(num-1) is exactly i (3D:328) */
+                    const double v[7] = {(double)i, (double)j, (double)k, u1[c], u2[c], u3[c], vmag[c]};
+                    for (int a = 0; a < 7; a++) {
+                        p += fmt10(p, v[a]);
+                        if (a < 6) { *p++ = ','; *p++ = ' '; }
+                    }
+                    *p++ = '\n';
+                }
+            lens[i - i0] = (size_t)(p - bufs[i - i0]);
+        }
+        for (int i = i0; i < i1; i++)
+            if (fwrite(bufs[i - i0], 1, lens[i - i0], fp) != lens[i - i0]) { printf("Error writing file!\n"); exit(1); }
+    }
+    for (int t = 0; t < T; t++) free(bufs[t]);
+    free(bufs); free(lens);
     fclose(fp);
 }
 

@@ -9,6 +9,11 @@ where /root/reference exists; the GPU box only reads the committed outputs).
    reference (oracle/_ref binaries, see oracle/build_ref.py) after n iterations, per configuration.
    A hash is enough because the parity target is bit-exact.
 3. ref_f_N12_Re100_300.npy  <- one small raw lattice, so a mismatch can be localised.
+4. solution_n50_re100_default.npz  <- the reference's DEFAULT configuration (BASELINE config 1: N=50,
+   Re=100, TRT, THRESH=1e-12) run to convergence with `oracle/_ref/lbm3d_ref_N50_... main` (the
+   reference's own main(), 131 000 iterations, ~25 min on 8 cores): the printed values of its
+   Solution_*.dat as int32 = round(value * 1e10), the iteration count and the printed residuals.
+   Only rebuilt with --default-run (slow).
 """
 import hashlib
 import json
@@ -44,7 +49,30 @@ HASH_CASES = [
 ]
 
 
+def default_run():
+    import subprocess
+    import tempfile
+    exe = O.ref_binary(N=50, Re=100)
+    with tempfile.TemporaryDirectory() as tmp:
+        log = subprocess.run([exe, "main"], cwd=tmp, capture_output=True, text=True, check=True).stdout
+        dat = os.path.join(tmp, "Solution_n=50Re=100_DIAG=0_2RT_M=0.250.dat")
+        md5 = hashlib.md5(open(dat, "rb").read()).hexdigest()
+        with open(dat) as fh:
+            header = fh.readline().rstrip("\n")
+            data = np.loadtxt(fh, delimiter=",")
+    its = [l for l in log.splitlines() if l.startswith("Iteration")]
+    dfs = [l.split("\t")[1] for l in log.splitlines() if l.startswith("df")]
+    q = lambda a: np.round(a * 1e10).astype(np.int32)
+    np.savez_compressed(os.path.join(HERE, "solution_n50_re100_default.npz"), header=np.array(header), u_e10=q(data[:, 3]),
+                        v_e10=q(data[:, 4]), w_e10=q(data[:, 5]), vmag_e10=q(data[:, 6]),
+                        iterations=np.array(int(its[-1].split()[1].rstrip(":"))), df_final=np.array(dfs[-1]),
+                        df0=np.array(dfs[0]), dat_md5=np.array(md5))
+
+
 def main():
+    if "--default-run" in sys.argv:
+        default_run()
+        return
     with open(DAT) as fh:
         header = fh.readline().rstrip("\n")
         data = np.loadtxt(fh, delimiter=",")

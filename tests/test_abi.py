@@ -98,3 +98,12 @@ def test_product_does_not_reference_the_oracle():
                     os.path.join(dirpath, fn)
     out = subprocess.run(["ldd", os.path.join(pkg, "liblbm_b200.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_fast_formatter_equals_printf(tmp_path):
+    """host/fmt10.h (used by the Tecplot writer) must produce printf("%.10f") byte for byte."""
+    exe = str(tmp_path / "fmt10_check")
+    subprocess.check_call(["gcc", "-O2", "-I", os.path.join(ROOT, "cfd-codes_b200", "host"), "-o", exe,
+                           os.path.join(ROOT, "tests", "fmt10_check.c"), "-lm"])
+    r = subprocess.run([exe, "1500000"], capture_output=True, text=True)
+    assert r.returncode == 0 and "fmt10 ok" in r.stdout, r.stdout[-500:]

@@ -57,3 +57,25 @@ def test_lbm2d_cavity_outputs(tmp_path):
     x = np.fromfile(tmp_path / "Re=50_N=40_M=60_x.bin").reshape(60, 40)
     rho = np.fromfile(tmp_path / "Re=50_N=40_M=60_rho.bin")
     assert np.array_equal(x[0], 0.5 + np.arange(40)) and u[59].min() > 0.0 and u[59].mean() > 0.05 and abs(rho.mean() - 1.0) < 1e-3
+
+
+def test_default_configuration_drop_in(tmp_path):
+    """BASELINE config 1: `lbm3d_cavity` with NO flags = the reference's `./a.out` (N=50, Re=100, TRT,
+    THRESH=1e-12).  The reference needs 131 000 iterations / 22 minutes on 8 cores; its
+    result was recorded by tests/golden/make_golden.py --default-run.  Same iteration count, same
+    printed residuals, every printed digit of the 125 000 x 4 output values identical."""
+    g = np.load(os.path.join(GOLD, "solution_n50_re100_default.npz"))
+    r = subprocess.run([EXE3], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    out = r.stdout
+    for line in ("Re =\t100", "Re_g =\t1.961e+00", "U =\t1.000e-01", "N =\t50", "tau =\t6.530e-01", "nu =\t5.100e-02",
+                 "M =\t1.732e-01"):                     # the banner of SURVEY App. C
+        assert line + "\n" in out, line
+    assert "\nIteration 0:\ndf:\t%s\n" % str(g["df0"]) in out
+    its = re.findall(r"\nIteration (\d+):\ndf/df0:\t(\S+)\n", out)
+    assert its[-1] == (str(int(g["iterations"])), str(g["df_final"]))
+    with open(tmp_path / "Solution_n=50Re=100_DIAG=0_2RT_M=0.250.dat") as fh:
+        assert fh.readline().rstrip("\n") == str(g["header"])
+        data = np.loadtxt(fh, delimiter=",")
+    for col, name in ((3, "u"), (4, "v"), (5, "w"), (6, "vmag")):
+        assert np.array_equal(np.round(data[:, col] * 1e10).astype(np.int32), g[name + "_e10"]), name

@@ -103,6 +103,20 @@ def test_block_shape_does_not_change_the_field(lbm):
             assert r == pytest.approx(rref, rel=1e-13)
 
 
+@pytest.mark.parametrize("cfg", [dict(N=12, Re=100), dict(N=34, Re=200, DIAG=1), dict(N=20, Re=20, METHOD=0, GAMMA=0.5),
+                                 dict(N=130, Re=500)], ids=lambda c: "N%d" % c["N"])
+def test_two_cells_per_thread_kernel_gives_the_same_bits(lbm, oracle, cfg):
+    """The 128-bit variant (option vec2: two x-adjacent cells per thread, double2 loads/stores)."""
+    o = oracle.Oracle3D(threads=8, **cfg)
+    o.step(40)
+    with lbm.Cavity3D(**cfg) as sim:
+        sim.set_option("vec2", 1)
+        for n in (1, 2, 3, 34):
+            sim.step(n)
+        assert np.array_equal(bits(sim.f()), bits(o.f()))
+        assert sim.residual() == pytest.approx(o.last_diff, rel=RESID_RTOL)
+
+
 def test_restart_from_host_distributions(lbm, oracle):
     """lbm_set_f: continue from the reference's two buffers (f2 newest, f1 the one to be overwritten)."""
     cfg = dict(N=14, Re=100)

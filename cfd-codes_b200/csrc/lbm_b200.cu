@@ -92,7 +92,7 @@ struct lbm_ctx {
     int dev = 0;
     cudaStream_t s_main = nullptr, s_halo = nullptr;
     bool own_main = false;
-    cudaEvent_t ev_bnd = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_bnd = nullptr, ev_halo = nullptr, ev_main = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     bool halo_pending = false;  // ev_halo has been recorded and not yet waited on by s_main
 
     int N = 0, nzl = 0, k0 = 0, k1 = 0;
@@ -199,37 +199,37 @@ static lbm3d::KP make_kp(const lbm_ctx *c) {
 }
 
 template <int MODE>
-static void launch_step_mode(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, dim3 blk) {
+static void launch_step_mode(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, dim3 blk, cudaStream_t st) {
     const bool g1 = (c->prm.GAMMA == 1.0);  // x * (1.0 / 1.0) == x: the specialised kernel drops the multiply
     if (c->prm.METHOD == 1) {
-        if (g1) lbm3d::k_step<1, MODE, true><<<grid, blk, 0, c->s_main>>>(p);
-        else    lbm3d::k_step<1, MODE, false><<<grid, blk, 0, c->s_main>>>(p);
+        if (g1) lbm3d::k_step<1, MODE, true><<<grid, blk, 0, st>>>(p);
+        else    lbm3d::k_step<1, MODE, false><<<grid, blk, 0, st>>>(p);
     } else {
-        if (g1) lbm3d::k_step<0, MODE, true><<<grid, blk, 0, c->s_main>>>(p);
-        else    lbm3d::k_step<0, MODE, false><<<grid, blk, 0, c->s_main>>>(p);
+        if (g1) lbm3d::k_step<0, MODE, true><<<grid, blk, 0, st>>>(p);
+        else    lbm3d::k_step<0, MODE, false><<<grid, blk, 0, st>>>(p);
     }
     c->launches++;
 }
 
-static void launch_step(lbm_ctx *c, int mode, const lbm3d::KP &p, dim3 grid, dim3 blk) {
+static void launch_step(lbm_ctx *c, int mode, const lbm3d::KP &p, dim3 grid, dim3 blk, cudaStream_t st) {
     if (mode == lbm3d::MODE_STEP && c->vec2 && (c->N % 2) == 0) {
         const bool g1 = (c->prm.GAMMA == 1.0);
         dim3 g2((c->N / 2 + blk.x - 1) / blk.x, grid.y, grid.z);
         if (c->prm.METHOD == 1) {
-            if (g1) lbm3d::k_step_x2<1, true><<<g2, blk, 0, c->s_main>>>(p);
-            else    lbm3d::k_step_x2<1, false><<<g2, blk, 0, c->s_main>>>(p);
+            if (g1) lbm3d::k_step_x2<1, true><<<g2, blk, 0, st>>>(p);
+            else    lbm3d::k_step_x2<1, false><<<g2, blk, 0, st>>>(p);
         } else {
-            if (g1) lbm3d::k_step_x2<0, true><<<g2, blk, 0, c->s_main>>>(p);
-            else    lbm3d::k_step_x2<0, false><<<g2, blk, 0, c->s_main>>>(p);
+            if (g1) lbm3d::k_step_x2<0, true><<<g2, blk, 0, st>>>(p);
+            else    lbm3d::k_step_x2<0, false><<<g2, blk, 0, st>>>(p);
         }
         c->launches++;
         return;
     }
     switch (mode) {
-        case lbm3d::MODE_STEP: launch_step_mode<lbm3d::MODE_STEP>(c, p, grid, blk); break;
-        case lbm3d::MODE_STEP_STOREF: launch_step_mode<lbm3d::MODE_STEP_STOREF>(c, p, grid, blk); break;
-        case lbm3d::MODE_STEP_DIFF_STOREF: launch_step_mode<lbm3d::MODE_STEP_DIFF_STOREF>(c, p, grid, blk); break;
-        default: launch_step_mode<lbm3d::MODE_MATERIALISE>(c, p, grid, blk); break;
+        case lbm3d::MODE_STEP: launch_step_mode<lbm3d::MODE_STEP>(c, p, grid, blk, st); break;
+        case lbm3d::MODE_STEP_STOREF: launch_step_mode<lbm3d::MODE_STEP_STOREF>(c, p, grid, blk, st); break;
+        case lbm3d::MODE_STEP_DIFF_STOREF: launch_step_mode<lbm3d::MODE_STEP_DIFF_STOREF>(c, p, grid, blk, st); break;
+        default: launch_step_mode<lbm3d::MODE_MATERIALISE>(c, p, grid, blk, st); break;
     }
 }
 
@@ -297,24 +297,31 @@ static int run_iteration(lbm_ctx *c, int mode) {
     if (!multi || !real) {
         if (multi && c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
         p.kl0 = 0; p.kstride = 1; p.partial_base = 0;
-        launch_step(c, mode, p, dim3(gxy.x, gxy.y, c->nzl), blk);
+        launch_step(c, mode, p, dim3(gxy.x, gxy.y, c->nzl), blk, c->s_main);
     } else {
-        // boundary planes first (they need the ghosts received after the previous iteration and
-        // feed this iteration's exchange), then the interior overlaps the NCCL transfer.
-        if (c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
+        // Two streams.  s_halo (high priority): the two slab-boundary planes, then the NCCL exchange
+        // of what they produced.  s_main: the interior planes, concurrently (the boundary launch is
+        // too small to fill the GPU on its own, and the exchange hides behind the interior).
+        //   interior(t) needs boundary(t-1): it reads planes 0 / nzl-1 of the source lattice and
+        //                overwrites planes 1 / nzl-2 of the lattice boundary(t-1) was reading;
+        //   boundary(t) needs interior(t-1) (same two reasons, mirrored) and exchange(t-1) (ghosts;
+        //                stream order on s_halo).
+        CK(cudaStreamWaitEvent(c->s_main, c->ev_bnd, 0));   // the record of iteration t-1 (no-op the first time)
+        CK(cudaEventRecord(c->ev_main, c->s_main));         // everything queued on s_main so far, incl. interior(t-1)
+        CK(cudaStreamWaitEvent(c->s_halo, c->ev_main, 0));
         const int nb = c->nzl >= 2 ? 2 : 1;
         p.kl0 = 0; p.kstride = c->nzl >= 2 ? c->nzl - 1 : 1; p.partial_base = 0;
-        launch_step(c, mode, p, dim3(gxy.x, gxy.y, nb), blk);
-        CK(cudaEventRecord(c->ev_bnd, c->s_main));
-        CK(cudaStreamWaitEvent(c->s_halo, c->ev_bnd, 0));
+        launch_step(c, mode, p, dim3(gxy.x, gxy.y, nb), blk, c->s_halo);
+        CK(cudaEventRecord(c->ev_bnd, c->s_halo));
         int rc = halo_exchange(c, c->lat[src_i ^ 1], c->s_halo);
         if (rc) return rc;
         CK(cudaEventRecord(c->ev_halo, c->s_halo));
         c->halo_pending = true;
         if (c->nzl > 2) {
             p.kl0 = 1; p.kstride = 1; p.partial_base = (int)(bpp * nb);
-            launch_step(c, mode, p, dim3(gxy.x, gxy.y, c->nzl - 2), blk);
+            launch_step(c, mode, p, dim3(gxy.x, gxy.y, c->nzl - 2), blk, c->s_main);
         }
+        if (mode == lbm3d::MODE_STEP_DIFF_STOREF) CK(cudaStreamWaitEvent(c->s_main, c->ev_bnd, 0));  // its block partials
     }
     CK(cudaGetLastError());
     if (real) {
@@ -629,6 +636,7 @@ int lbm_destroy(lbm_ctx *c) {
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -769,6 +777,7 @@ int lbm_create(const lbm_params *p, lbm_ctx **out) {
         CKD(cudaStreamCreateWithPriority(&c->s_halo, cudaStreamNonBlocking, hi));
         CKD(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
         CKD(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+        CKD(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
         if ((rc = nccl_load())) { lbm_destroy(c); return rc; }
         ncclUniqueId id;
         memcpy(&id, p->nccl_id, LBM_NCCL_ID_BYTES);
@@ -876,6 +885,7 @@ int lbm_sync(lbm_ctx *c) {
 int lbm_get_f(lbm_ctx *c, double *host_full) {
     if (!c || !host_full) return fail(LBM_ERR_INVALID, "null argument");
     CK(cudaSetDevice(c->dev));
+    if (c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
     if (c->prm.dim == 2) return copy_dist2d(c, host_full, true);
     int rc = materialise_F(c);
     if (rc) return rc;
@@ -954,6 +964,7 @@ int lbm_set_f(lbm_ctx *c, const double *host_f, const double *host_f_prev) {
 int lbm_macrovars(lbm_ctx *c, double *u1, double *u2, double *u3, double *rho, double *vmag) {
     if (!c) return fail(LBM_ERR_INVALID, "null context");
     CK(cudaSetDevice(c->dev));
+    if (c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
     if (c->prm.dim == 2) return macrovars2d(c, u1, u2, rho, vmag);
     int rc = materialise_F(c);
     if (rc) return rc;

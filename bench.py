@@ -196,6 +196,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--block-x", type=int, default=0)
     ap.add_argument("--block-y", type=int, default=0)
+    ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"],
+                    help="multi-GPU halo transport: NCCL send/recv (default) or the fused direct NVLink stores")
     ap.add_argument("--workload", default="cavity3d", choices=["cavity3d", "d2q9"],
                     help="d2q9: BASELINE config 5 (8192^2 D2Q9 variant of the kernel, 1 GPU; extra line, not the headline)")
     a = ap.parse_args()
@@ -253,6 +255,12 @@ def main():
     N = a.grid or (256 if world == 1 else 512)
     sim = lbm.Cavity3D(N=N, Re=a.Re, UMAX=0.1, METHOD=1, rank=rank, nranks=world, device=local_rank,
                        track_residual=True, nccl_id=nccl_id)
+    if multi and a.halo == "p2p":
+        import cfd_codes_b200.distributed as D
+        if not dist.is_initialized():
+            raise RuntimeError("process group missing")
+        # the blobs travel as CPU tensors: needs a CPU-capable backend
+        D.connect_direct_halo_via(sim, dist, dev)
     if a.block_x:
         sim.set_option("block_x", a.block_x)
     if a.block_y:
@@ -361,7 +369,7 @@ def main():
                        "grid": N, "Re": a.Re, "UMAX": 0.1, "method": "TRT", "iterations_per_step": block,
                        "step": "one residual block of the reference loop: %d iterations + diff" % block,
                        "l2": "inputs larger than L2: %.2f GB lattice per GPU vs 126 MB" % (19 * 8 * cells / world / 1e9),
-                       "parallelism": "z-slab x%d" % world, "residual_last": res},
+                       "parallelism": "z-slab x%d" % world, "halo": a.halo if world > 1 else None, "residual_last": res},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "wall_s_timed_region": t_wall,
         }

@@ -29,10 +29,11 @@ LIB_PATH = os.path.join(HERE, "liblbm_b200.so")
 
 LBM_OK, LBM_ERR_INVALID, LBM_ERR_CUDA, LBM_ERR_UNSTABLE, LBM_ERR_NCCL, LBM_ERR_NOMEM = range(6)
 NCCL_ID_BYTES = 128
+PEER_BLOB_BYTES = 320
 
 # every symbol include/lbm_b200.h declares
 ABI_SYMBOLS = [
-    "lbm_default_params", "lbm_nccl_unique_id", "lbm_create", "lbm_step", "lbm_step_timed", "lbm_timer_start",
+    "lbm_default_params", "lbm_nccl_unique_id", "lbm_create", "lbm_peer_export", "lbm_peer_connect", "lbm_step", "lbm_step_timed", "lbm_timer_start",
     "lbm_timer_stop", "lbm_residual",
     "lbm_get_f", "lbm_set_f", "lbm_macrovars", "lbm_sync", "lbm_get_info", "lbm_set_option", "lbm_destroy",
     "lbm_last_error", "lbm_version",
@@ -86,6 +87,8 @@ def load_library(path=None):
     L.lbm_default_params.restype = None
     L.lbm_nccl_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
     L.lbm_create.argtypes = [C.POINTER(LbmParams), C.POINTER(vp)]
+    L.lbm_peer_export.argtypes = [vp, C.POINTER(C.c_ubyte)]
+    L.lbm_peer_connect.argtypes = [vp, C.c_char_p, C.c_char_p]
     L.lbm_step.argtypes = [vp, C.c_longlong]
     L.lbm_step_timed.argtypes = [vp, C.c_longlong, C.POINTER(C.c_float)]
     L.lbm_timer_start.argtypes = [vp]
@@ -100,7 +103,7 @@ def load_library(path=None):
     L.lbm_destroy.argtypes = [vp]
     L.lbm_last_error.restype = C.c_char_p
     L.lbm_version.restype = C.c_char_p
-    for name in ("lbm_nccl_unique_id", "lbm_create", "lbm_step", "lbm_step_timed", "lbm_timer_start", "lbm_timer_stop",
+    for name in ("lbm_nccl_unique_id", "lbm_create", "lbm_peer_export", "lbm_peer_connect", "lbm_step", "lbm_step_timed", "lbm_timer_start", "lbm_timer_stop",
                  "lbm_residual", "lbm_get_f",
                  "lbm_set_f", "lbm_macrovars", "lbm_sync", "lbm_get_info", "lbm_set_option", "lbm_destroy"):
         getattr(L, name).restype = C.c_int
@@ -159,6 +162,15 @@ class Cavity3D:
         _check(L.lbm_create(C.byref(p), C.byref(h)))
         self._h = h
         self._L = L
+
+    # -- direct NVLink halo (optional) ----------------------------------------------------------------
+    def peer_export(self):
+        buf = (C.c_ubyte * PEER_BLOB_BYTES)()
+        _check(self._L.lbm_peer_export(self._h, buf))
+        return bytes(buf)
+
+    def peer_connect(self, below, above):
+        _check(self._L.lbm_peer_connect(self._h, below, above))
 
     # -- the reference's time loop ---------------------------------------------------------------
     def step(self, n=1):

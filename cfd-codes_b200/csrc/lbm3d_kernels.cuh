@@ -68,6 +68,13 @@ struct KP {
     long long N2, PS, FS;
     double omega, omegam, omomega, gammainv;   // 3D:21,23,30,40
     double ulid, vlid, wlid, vfrac, third, sixth;  // 3D:183-191, 386, 41-42
+    // Direct NVLink halo (PEER kernels only): the neighbours' ghost planes of the lattice being
+    // written, mapped into this process (CUDA IPC / peer access); indexed by j*N + i.
+    double *peer_dn[5];          // rank-1's top ghost plane for populations {6,10,12,15,17}; null at the bottom rank
+    double *peer_up[5];          // rank+1's bottom ghost plane for {5,9,11,16,18}; null at the top rank
+    unsigned int *done_count;    // blocks of this launch that have finished their peer stores
+    long long *sig_dn, *sig_up;  // the neighbours' arrival flags (in THEIR memory), null if absent
+    long long sig_value;         // iteration stamp to publish
 };
 
 // ---- global memory access policy (tuned with tools/ab_variants.sh; default = plain LDG/STG) ------
@@ -267,7 +274,11 @@ __device__ __forceinline__ double block_sum(double v) {
 #define LBM_STEP_MAX_THREADS 128
 #define LBM_STEP_MIN_BLOCKS 5
 #endif
-template <int METHOD, int MODE, bool G1>
+// PEER (slab-boundary planes of a multi-GPU run with the direct NVLink halo): the thread also stores
+// the five face-crossing post-collision populations of its cell straight into the neighbour GPU's
+// ghost plane (peer memory), and the last block to finish publishes the iteration stamp in the
+// neighbours' arrival flags -- compute and exchange in ONE kernel, no send/recv.
+template <int METHOD, int MODE, bool G1, bool PEER = false>
 __global__ void __launch_bounds__(LBM_STEP_MAX_THREADS, LBM_STEP_MIN_BLOCKS) k_step(const __grid_constant__ KP p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -332,6 +343,35 @@ __global__ void __launch_bounds__(LBM_STEP_MAX_THREADS, LBM_STEP_MIN_BLOCKS) k_s
             if (neg) atomicOr(p.flag, 1);
 #pragma unroll
             for (int q = 0; q < Q; q++) lbm_store(p.dstq[q] + cell, f[q]);
+            if (PEER) {
+                if (kl == 0 && p.peer_dn[0] != nullptr) {          // cz = -1 populations leave through the bottom face
+                    p.peer_dn[0][rowcell] = f[6];  p.peer_dn[1][rowcell] = f[10]; p.peer_dn[2][rowcell] = f[12];
+                    p.peer_dn[3][rowcell] = f[15]; p.peer_dn[4][rowcell] = f[17];
+                }
+                if (kl == p.nzl - 1 && p.peer_up[0] != nullptr) {  // cz = +1 populations leave through the top face
+                    p.peer_up[0][rowcell] = f[5];  p.peer_up[1][rowcell] = f[9];  p.peer_up[2][rowcell] = f[11];
+                    p.peer_up[3][rowcell] = f[16]; p.peer_up[4][rowcell] = f[18];
+                }
+            }
+        }
+    }
+
+    if (PEER) {
+        // publish: every block fences its peer stores system-wide, the last one raises the flags
+        __shared__ bool last;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+            last = (atomicAdd(p.done_count, 1u) == total - 1);
+        }
+        __syncthreads();
+        if (last && threadIdx.x == 0 && threadIdx.y == 0) {
+            *p.done_count = 0;
+            __threadfence_system();
+            if (p.sig_dn) *reinterpret_cast<volatile long long *>(p.sig_dn) = p.sig_value;
+            if (p.sig_up) *reinterpret_cast<volatile long long *>(p.sig_up) = p.sig_value;
+            __threadfence_system();
         }
     }
 
@@ -470,6 +510,20 @@ __global__ void __launch_bounds__(256) k_macrovars(const double *__restrict__ F,
     if (u2) u2[n] = v;
     if (u3) u3[n] = w;
     if (vmag) vmag[n] = sqrt((u * u + v * v) + w * w);  // 3D:735
+}
+
+// Wait (one thread) until both neighbours have published `need` in this GPU's arrival flags, i.e.
+// their slab-boundary kernels of the previous iteration -- the ones that fill my ghost planes and
+// read the ghost planes I am about to overwrite -- are complete.  Bounded: after `timeout` cycles the
+// error bit 4 is raised instead of hanging the GPU.
+__global__ void k_wait_arrivals(const volatile long long *sig, long long need_dn, long long need_up, int *flag,
+                                long long timeout) {
+    const long long t0 = clock64();
+    while (sig[0] < need_dn || sig[1] < need_up) {
+        if (clock64() - t0 > timeout) { atomicOr(flag, 4); break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
 }
 
 // Second stage of the residual: one block sums the block partials in a fixed order.

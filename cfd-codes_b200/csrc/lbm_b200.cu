@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <vector>
 
@@ -131,6 +132,16 @@ struct lbm_ctx {
     long long plain_iters = 0;
     int block_x = 0, block_y = 0;
     int vec2 = 0;  // 1: plain iterations use the two-cells-per-thread 128-bit kernel (N even)
+    // direct NVLink halo (lbm_peer_connect): neighbours' lattices / arrival flags mapped here
+    bool p2p = false;
+    long long p2p_base = 0;               // iteration count at which the direct halo was switched on
+    long long *sig = nullptr;             // my arrival flags: [0] written by rank-1, [1] by rank+1
+    unsigned int *done_count = nullptr;
+    double *peer_lat[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [side 0 = below, 1 = above][lattice]
+    long long *peer_sig[2] = {nullptr, nullptr};
+    void *peer_ipc[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // opened IPC mappings to close
+    int peer_nzl[2] = {0, 0};
+    long long peer_PS[2] = {0, 0};
     bool host_local = false;  // host arrays are compact local slabs instead of full LU4/LU3 arrays
     ncclComm_t comm = nullptr;
 };
@@ -196,6 +207,27 @@ static lbm3d::KP make_kp(const lbm_ctx *c) {
     p.partials = c->partials;
     p.Fbuf = c->Fbuf;
     return p;
+}
+
+struct PeerBlob {   // what lbm_peer_export hands to the neighbours (<= LBM_PEER_BLOB_BYTES)
+    int magic, pid, dev, nzl;
+    long long PS, pad;
+    cudaIpcMemHandle_t lat[2], sig;
+    void *raw_lat[2], *raw_sig;
+};
+static_assert(sizeof(PeerBlob) <= LBM_PEER_BLOB_BYTES, "PeerBlob too large");
+
+template <int MODE>
+static void launch_step_peer(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, dim3 blk, cudaStream_t st) {
+    const bool g1 = (c->prm.GAMMA == 1.0);
+    if (c->prm.METHOD == 1) {
+        if (g1) lbm3d::k_step<1, MODE, true, true><<<grid, blk, 0, st>>>(p);
+        else    lbm3d::k_step<1, MODE, false, true><<<grid, blk, 0, st>>>(p);
+    } else {
+        if (g1) lbm3d::k_step<0, MODE, true, true><<<grid, blk, 0, st>>>(p);
+        else    lbm3d::k_step<0, MODE, false, true><<<grid, blk, 0, st>>>(p);
+    }
+    c->launches++;
 }
 
 template <int MODE>
@@ -311,10 +343,39 @@ static int run_iteration(lbm_ctx *c, int mode) {
         CK(cudaStreamWaitEvent(c->s_halo, c->ev_main, 0));
         const int nb = c->nzl >= 2 ? 2 : 1;
         p.kl0 = 0; p.kstride = c->nzl >= 2 ? c->nzl - 1 : 1; p.partial_base = 0;
-        launch_step(c, mode, p, dim3(gxy.x, gxy.y, nb), blk, c->s_halo);
-        CK(cudaEventRecord(c->ev_bnd, c->s_halo));
-        int rc = halo_exchange(c, c->lat[src_i ^ 1], c->s_halo);
-        if (rc) return rc;
+        if (!c->p2p) {
+            launch_step(c, mode, p, dim3(gxy.x, gxy.y, nb), blk, c->s_halo);
+            CK(cudaEventRecord(c->ev_bnd, c->s_halo));
+            int rc = halo_exchange(c, c->lat[src_i ^ 1], c->s_halo);
+            if (rc) return rc;
+        } else {
+            // Direct NVLink halo: wait until both neighbours finished their boundary kernels of the
+            // previous iteration (they filled my ghosts and are done reading the ghosts I overwrite
+            // now), then ONE kernel computes the boundary planes, stores the face-crossing
+            // populations into the neighbours' ghost planes and publishes this iteration's stamp.
+            const long long rel = t - c->p2p_base;
+            const int r = c->prm.rank, P = c->prm.nranks;
+            lbm3d::k_wait_arrivals<<<1, 1, 0, c->s_halo>>>(c->sig, r > 0 ? rel : 0, r + 1 < P ? rel : 0, c->d_flag,
+                                                            20000000000LL);
+            c->launches++;
+            const int dsti = src_i ^ 1;
+            for (int a = 0; a < 5; a++) {
+                p.peer_dn[a] = r > 0 ? c->peer_lat[0][dsti] + (long long)Q_DN[a] * c->peer_PS[0] + (long long)(c->peer_nzl[0] + 1) * c->N2
+                                     : nullptr;
+                p.peer_up[a] = r + 1 < P ? c->peer_lat[1][dsti] + (long long)Q_UP[a] * c->peer_PS[1] : nullptr;
+            }
+            p.done_count = c->done_count;
+            p.sig_dn = r > 0 ? c->peer_sig[0] + 1 : nullptr;      // I am the neighbour "above" rank-1
+            p.sig_up = r + 1 < P ? c->peer_sig[1] + 0 : nullptr;  // and the neighbour "below" rank+1
+            p.sig_value = rel + 1;
+            const dim3 grid(gxy.x, gxy.y, nb);
+            switch (mode) {
+                case lbm3d::MODE_STEP: launch_step_peer<lbm3d::MODE_STEP>(c, p, grid, blk, c->s_halo); break;
+                case lbm3d::MODE_STEP_STOREF: launch_step_peer<lbm3d::MODE_STEP_STOREF>(c, p, grid, blk, c->s_halo); break;
+                default: launch_step_peer<lbm3d::MODE_STEP_DIFF_STOREF>(c, p, grid, blk, c->s_halo); break;
+            }
+            CK(cudaEventRecord(c->ev_bnd, c->s_halo));
+        }
         CK(cudaEventRecord(c->ev_halo, c->s_halo));
         c->halo_pending = true;
         if (c->nzl > 2) {
@@ -354,7 +415,15 @@ static int materialise_F(lbm_ctx *c) {
         c->f_valid = true;
         return LBM_OK;
     }
-    return run_iteration(c, lbm3d::MODE_MATERIALISE);
+    rc = run_iteration(c, lbm3d::MODE_MATERIALISE);
+    if (rc) return rc;
+    if (c->p2p) {
+        // With the direct halo a neighbour may already be one iteration ahead and would overwrite the
+        // ghost planes this kernel reads; a collective point after it keeps everybody behind it
+        // (so lbm_get_f / lbm_macrovars on a stale F buffer are collective calls in this mode).
+        NK(g_nccl.AllReduce(c->d_red + 1, c->d_red + 1, 1, ncclDouble, ncclSum, c->comm, c->s_main));
+    }
+    return LBM_OK;
 }
 
 static int poll_flag(lbm_ctx *c) {
@@ -362,7 +431,8 @@ static int poll_flag(lbm_ctx *c) {
     CK(cudaMemcpyAsync(&flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->s_main));
     CK(cudaStreamSynchronize(c->s_main));
     if (c->s_halo) CK(cudaStreamSynchronize(c->s_halo));
-    if (flag) c->unstable = true;
+    if (flag & 4) return fail(LBM_ERR_CUDA, "direct halo: timed out waiting for a neighbour GPU's arrival flag");
+    if (flag & 1) c->unstable = true;
     if (c->unstable) return fail(LBM_ERR_UNSTABLE, "Error: negative feq.  Therefore, unstable.");
     return LBM_OK;
 }
@@ -625,8 +695,18 @@ int lbm_nccl_unique_id(unsigned char out[LBM_NCCL_ID_BYTES]) {
 int lbm_destroy(lbm_ctx *c) {
     if (!c) return LBM_OK;
     cudaSetDevice(c->dev);
+    if (c->p2p && c->s_halo && c->steps > c->p2p_base) {
+        // the neighbours' last boundary kernels store into my ghost planes: let them land first
+        const long long rel = c->steps - c->p2p_base;
+        lbm3d::k_wait_arrivals<<<1, 1, 0, c->s_halo>>>(c->sig, c->prm.rank > 0 ? rel : 0,
+                                                        c->prm.rank + 1 < c->prm.nranks ? rel : 0, c->d_flag, 4000000000LL);
+    }
     if (c->s_main) cudaStreamSynchronize(c->s_main);
     if (c->s_halo) cudaStreamSynchronize(c->s_halo);
+    for (int side = 0; side < 2; side++)
+        for (int a = 0; a < 3; a++)
+            if (c->peer_ipc[side][a]) cudaIpcCloseMemHandle(c->peer_ipc[side][a]);
+    cudaFree(c->sig); cudaFree(c->done_count);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     cudaFree(c->lat_alloc[0]); cudaFree(c->lat_alloc[1]); cudaFree(c->Fbuf); cudaFree(c->side);
     cudaFree(c->partials); cudaFree(c->d_red); cudaFree(c->d_flag);
@@ -793,6 +873,77 @@ int lbm_create(const lbm_params *p, lbm_ctx **out) {
     rc = (p->dim == 3) ? create3d(c) : create2d(c);
     if (rc) { lbm_destroy(c); return rc; }
     *out = c;
+    return LBM_OK;
+}
+
+
+int lbm_peer_export(lbm_ctx *c, unsigned char blob[LBM_PEER_BLOB_BYTES]) {
+    if (!c || !blob) return fail(LBM_ERR_INVALID, "null argument");
+    if (c->prm.dim != 3 || c->prm.nranks < 2) return fail(LBM_ERR_INVALID, "the direct halo needs dim=3 and nranks > 1");
+    CK(cudaSetDevice(c->dev));
+    int rc;
+    if (!c->sig) {
+        if ((rc = dev_alloc(c, &c->sig, 2))) return rc;
+        if ((rc = dev_alloc(c, &c->done_count, 1))) return rc;
+        CK(cudaMemset(c->sig, 0, 2 * sizeof(long long)));
+        CK(cudaMemset(c->done_count, 0, sizeof(unsigned int)));
+    }
+    PeerBlob b;
+    memset(&b, 0, sizeof b);
+    b.magic = 0x4c424d50; b.pid = (int)getpid(); b.dev = c->dev; b.nzl = c->nzl; b.PS = c->PS; b.pad = c->pad;
+    CK(cudaIpcGetMemHandle(&b.lat[0], c->lat_alloc[0]));
+    CK(cudaIpcGetMemHandle(&b.lat[1], c->lat_alloc[1]));
+    CK(cudaIpcGetMemHandle(&b.sig, c->sig));
+    b.raw_lat[0] = c->lat_alloc[0]; b.raw_lat[1] = c->lat_alloc[1]; b.raw_sig = c->sig;
+    memset(blob, 0, LBM_PEER_BLOB_BYTES);
+    memcpy(blob, &b, sizeof b);
+    return LBM_OK;
+}
+
+static int peer_open(lbm_ctx *c, int side, const unsigned char *blob) {
+    PeerBlob b;
+    memcpy(&b, blob, sizeof b);
+    if (b.magic != 0x4c424d50) return fail(LBM_ERR_INVALID, "bad peer blob");
+    void *lat0 = nullptr, *lat1 = nullptr, *sg = nullptr;
+    if (b.pid == (int)getpid()) {  // same process (one thread per GPU): plain peer access
+        if (b.dev != c->dev) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, c->dev, b.dev));
+            if (!can) return fail(LBM_ERR_CUDA, "device %d cannot access device %d", c->dev, b.dev);
+            cudaError_t e = cudaDeviceEnablePeerAccess(b.dev, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(LBM_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        lat0 = b.raw_lat[0]; lat1 = b.raw_lat[1]; sg = b.raw_sig;
+    } else {
+        CK(cudaIpcOpenMemHandle(&lat0, b.lat[0], cudaIpcMemLazyEnablePeerAccess));
+        CK(cudaIpcOpenMemHandle(&lat1, b.lat[1], cudaIpcMemLazyEnablePeerAccess));
+        CK(cudaIpcOpenMemHandle(&sg, b.sig, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_ipc[side][0] = lat0; c->peer_ipc[side][1] = lat1; c->peer_ipc[side][2] = sg;
+    }
+    c->peer_lat[side][0] = (double *)lat0 + b.pad;
+    c->peer_lat[side][1] = (double *)lat1 + b.pad;
+    c->peer_sig[side] = (long long *)sg;
+    c->peer_nzl[side] = b.nzl;
+    c->peer_PS[side] = b.PS;
+    return LBM_OK;
+}
+
+int lbm_peer_connect(lbm_ctx *c, const unsigned char *below_blob, const unsigned char *above_blob) {
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    if (c->prm.dim != 3 || c->prm.nranks < 2) return fail(LBM_ERR_INVALID, "the direct halo needs dim=3 and nranks > 1");
+    if (!c->sig) return fail(LBM_ERR_INVALID, "call lbm_peer_export first");
+    const int r = c->prm.rank, P = c->prm.nranks;
+    if ((r > 0 && !below_blob) || (r + 1 < P && !above_blob)) return fail(LBM_ERR_INVALID, "missing neighbour blob");
+    CK(cudaSetDevice(c->dev));
+    int rc = poll_flag(c);  // drains both streams
+    if (rc) return rc;
+    if (r > 0 && (rc = peer_open(c, 0, below_blob))) return rc;
+    if (r + 1 < P && (rc = peer_open(c, 1, above_blob))) return rc;
+    CK(cudaMemset(c->sig, 0, 2 * sizeof(long long)));
+    c->p2p_base = c->steps;
+    c->p2p = true;
     return LBM_OK;
 }
 

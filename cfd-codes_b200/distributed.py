@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-from . import NCCL_ID_BYTES, nccl_unique_id, slab_range
+from . import NCCL_ID_BYTES, PEER_BLOB_BYTES, nccl_unique_id, slab_range
 
 
 def env_rank():
@@ -69,3 +69,34 @@ def allreduce_max(x):
     t = torch.tensor([float(x)], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def connect_direct_halo(sim):
+    """Switch a multi-GPU Cavity3D to the direct NVLink halo: all-gather the per-rank export blobs
+    (torch.distributed, CPU tensors) and connect each rank to its two z-neighbours."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    mine = torch.frombuffer(bytearray(sim.peer_export()), dtype=torch.uint8)
+    blobs = [torch.zeros(PEER_BLOB_BYTES, dtype=torch.uint8) for _ in range(world)]
+    dist.all_gather(blobs, mine)
+    below = bytes(blobs[rank - 1].tolist()) if rank > 0 else None
+    above = bytes(blobs[rank + 1].tolist()) if rank + 1 < world else None
+    dist.barrier()
+    sim.peer_connect(below, above)
+    dist.barrier()
+
+
+def connect_direct_halo_via(sim, dist, device):
+    """Same as connect_direct_halo for a process group that only has the NCCL backend (bench.py):
+    the blobs are all-gathered as CUDA byte tensors."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    mine = torch.tensor(list(sim.peer_export()), dtype=torch.uint8, device=device)
+    blobs = [torch.zeros(PEER_BLOB_BYTES, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(blobs, mine)
+    below = bytes(blobs[rank - 1].cpu().tolist()) if rank > 0 else None
+    above = bytes(blobs[rank + 1].cpu().tolist()) if rank + 1 < world else None
+    dist.barrier()
+    sim.peer_connect(below, above)
+    dist.barrier()

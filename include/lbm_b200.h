@@ -33,6 +33,7 @@ extern "C" {
 #define LBM_ERR_NOMEM     5
 
 #define LBM_NCCL_ID_BYTES 128
+#define LBM_PEER_BLOB_BYTES 320
 
 typedef struct lbm_ctx lbm_ctx;
 
@@ -84,6 +85,16 @@ int lbm_nccl_unique_id(unsigned char out[LBM_NCCL_ID_BYTES]);
 /* Replaces allocate() + initialize() (3D:135-147, 172-206; 2D:127-158): device allocation,
  * derived constants, f = feq(rho=1, u=0) everywhere, lid velocity.  Collective when nranks > 1. */
 int lbm_create(const lbm_params *p, lbm_ctx **out);
+
+/* Optional direct NVLink halo for dim=3 multi-GPU runs (default transport: NCCL send/recv).
+ * Every rank calls lbm_peer_export and hands its blob to its two z-neighbours (any transport);
+ * every rank then calls lbm_peer_connect with the blobs of rank-1 / rank+1 (NULL at the ends),
+ * all at the same iteration count.  From then on the kernel that computes a slab-boundary plane also
+ * stores the five face-crossing populations straight into the neighbour GPU's ghost plane (CUDA IPC /
+ * peer access) and raises an arrival flag there: compute + exchange in one kernel, no send/recv.
+ * In this mode lbm_get_f / lbm_macrovars are collective calls when track_residual is 0. */
+int lbm_peer_export(lbm_ctx *c, unsigned char blob[LBM_PEER_BLOB_BYTES]);
+int lbm_peer_connect(lbm_ctx *c, const unsigned char *below_blob, const unsigned char *above_blob);
 
 /* Replaces n iterations of `macrocollideandstream(); HechtBC(f2); swap(&f1,&f2);`
  * (3D:94-100, 106-123; 2D: one streamCollide sweep of all rows per iteration, 2D:160-178).

@@ -42,7 +42,7 @@ def test_no_fma_contraction_in_step_kernels(lbm):
     that the TRT/BGK step kernels contain hundreds of DADD/DMUL and only a handful of DFMA."""
     out = subprocess.run(["cuobjdump", "-sass", lbm.LIB_PATH], capture_output=True, text=True).stdout
     secs = re.split(r"\n\s*Function : ", out)
-    sec = [x for x in secs if x.startswith("_ZN5lbm3d6k_stepILi1ELi0ELb1EEEvNS_2KPE")]
+    sec = [x for x in secs if x.startswith("_ZN5lbm3d6k_stepILi1ELi0ELb1ELb0EEEvNS_2KPE")]
     assert len(sec) == 1
     out = sec[0]
     n_fma = len(re.findall(r"\bDFMA\b", out))

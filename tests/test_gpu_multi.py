@@ -19,6 +19,10 @@ def ngpus():
 @pytest.mark.parametrize("world,args", [(2, ["--N", "32", "--steps", "40"]), (2, ["--N", "21", "--Re", "400", "--steps", "30"]),
                                         (2, ["--N", "16", "--method", "0", "--Re", "20", "--diag", "1", "--steps", "25"]),
                                         (4, ["--N", "30", "--steps", "30"]), (8, ["--N", "40", "--steps", "24"]),
+                                        (2, ["--halo", "p2p", "--N", "32", "--steps", "40"]),
+                                        (2, ["--halo", "p2p", "--N", "21", "--Re", "400", "--steps", "30", "--track", "0"]),
+                                        (4, ["--halo", "p2p", "--N", "30", "--steps", "30", "--diag", "1"]),
+                                        (8, ["--halo", "p2p", "--N", "40", "--steps", "24"]),
                                         (2, ["--dim", "2", "--N", "24", "--M", "41", "--Re", "40", "--steps", "50"]),
                                         (4, ["--dim", "2", "--N", "100", "--M", "30", "--Re", "100", "--steps", "40"])])
 def test_slab_run_matches_oracle(world, args):

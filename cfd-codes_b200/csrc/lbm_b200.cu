@@ -132,6 +132,12 @@ struct lbm_ctx {
     long long plain_iters = 0;
     int block_x = 0, block_y = 0;
     int vec2 = 0;  // 1: plain iterations use the two-cells-per-thread 128-bit kernel (N even)
+    // CUDA graphs for launch-bound grids (single GPU): GRAPH_LEN consecutive plain iterations per
+    // graph launch.  The kernel arguments of iteration t depend on (lattice parity, t mod 3), a
+    // 6-periodic pattern; GRAPH_LEN is a multiple of 6, so a graph captured in one phase leaves the
+    // context in the same phase and can be replayed back to back.
+    int graphs = -1;                         // -1 auto (small grids), 0 off, 1 on
+    cudaGraphExec_t graph_exec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // direct NVLink halo (lbm_peer_connect): neighbours' lattices / arrival flags mapped here
     bool p2p = false;
     long long p2p_base = 0;               // iteration count at which the direct halo was switched on
@@ -307,6 +313,47 @@ static int halo_exchange(lbm_ctx *c, double *L, cudaStream_t st) {
         }
     }
     NK(g_nccl.GroupEnd());
+    return LBM_OK;
+}
+
+static const int GRAPH_LEN = 60;
+
+static void drop_graphs(lbm_ctx *c) {
+    for (int k = 0; k < 6; k++)
+        if (c->graph_exec[k]) { cudaGraphExecDestroy(c->graph_exec[k]); c->graph_exec[k] = nullptr; }
+}
+
+static bool graphs_enabled(const lbm_ctx *c) {
+    if (c->prm.dim != 3 || c->prm.nranks != 1) return false;
+    if (c->graphs >= 0) return c->graphs != 0;
+    return c->FS <= (1LL << 21);   // auto: up to 128^3 cells the step is launch-latency-bound
+}
+
+static int run_iteration(lbm_ctx *c, int mode);
+
+// GRAPH_LEN plain iterations as one graph launch (captured on first use of each phase).
+static int run_graph_block(lbm_ctx *c) {
+    const int phase = (int)(c->steps % 3) * 2 + c->cur;
+    if (!c->graph_exec[phase]) {
+        const long long steps0 = c->steps, launches0 = c->launches;
+        const int cur0 = c->cur;
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(c->s_main, cudaStreamCaptureModeThreadLocal));
+        int rc = LBM_OK;
+        for (int k = 0; k < GRAPH_LEN && !rc; k++) rc = run_iteration(c, lbm3d::MODE_STEP);
+        cudaError_t e = cudaStreamEndCapture(c->s_main, &g);
+        c->steps = steps0; c->launches = launches0; c->cur = cur0;   // capturing executed nothing
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&c->graph_exec[phase], g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    }
+    CK(cudaGraphLaunch(c->graph_exec[phase], c->s_main));
+    c->steps += GRAPH_LEN;        // GRAPH_LEN is even and a multiple of 3: cur and the side slot phase are unchanged
+    c->launches += GRAPH_LEN;
+    c->f_valid = false;
+    c->residual_ready = false;
     return LBM_OK;
 }
 
@@ -719,6 +766,7 @@ int lbm_destroy(lbm_ctx *c) {
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    drop_graphs(c);
     for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->s_halo) cudaStreamDestroy(c->s_halo);
@@ -969,13 +1017,19 @@ int lbm_step(lbm_ctx *c, long long n) {
         sp.iters = n_plain;
         CK(cudaEventRecord(sp.a, c->s_main));
     }
+    const bool use_graphs = graphs_enabled(c);
     for (long long t = 0; t < n; t++) {
         int mode = lbm3d::MODE_STEP;
         if (track) {
             if (t == n - 1) mode = lbm3d::MODE_STEP_DIFF_STOREF;     // F(t) vs F(t-1): the reference's diff(f2, f1)
             else if (t == n - 2) mode = lbm3d::MODE_STEP_STOREF;     // leaves F(t-1) for the last iteration
         }
-        if ((rc = run_iteration(c, mode))) return rc;
+        if (use_graphs && t + GRAPH_LEN <= n_plain) {
+            if ((rc = run_graph_block(c))) return rc;
+            t += GRAPH_LEN - 1;
+        } else if ((rc = run_iteration(c, mode))) {
+            return rc;
+        }
         if (t == n_plain - 1) {
             CK(cudaEventRecord(sp.b, c->s_main));
             c->spans.push_back(sp);
@@ -1151,6 +1205,11 @@ int lbm_get_info(lbm_ctx *c, lbm_info *o) {
 
 int lbm_set_option(lbm_ctx *c, const char *key, long long value) {
     if (!c || !key) return fail(LBM_ERR_INVALID, "null argument");
+    drop_graphs(c);  // captured launches bake in the block shape and kernel variant
+    if (!strcmp(key, "graphs")) {
+        c->graphs = value < 0 ? -1 : (value != 0);
+        return LBM_OK;
+    }
     if (!strcmp(key, "block_x")) {
         const int lim = c->prm.dim == 2 ? 256 : 128;
         if (value < 0 || value > lim || (value % 32)) return fail(LBM_ERR_INVALID, "block_x must be a multiple of 32 <= %d", lim);

@@ -8,10 +8,11 @@
  * the C ABI of include/lbm_b200.h; this file contains no numerics except printf formatting.
  *
  *   lbm3d_cavity [--N 50] [--Re 100] [--UMAX 0.1] [--SAVETXT 1] [--THRESH 1E-12] [--METHOD 1]
- *                [--GAMMA 1.0] [--DIAG 0] [--MAGIC 0.25] [--MAXITER 1E8] [--skip 500] [--gpus 1]
+ *                [--GAMMA 1.0] [--DIAG 0] [--MAGIC 0.25] [--MAXITER 1E8] [--skip 500] [--gpus 1] [--halo 0]
  *
  * --gpus P (the reference's THREADS knob, 3D:15) runs P z-slabs, one host thread + one context
- * per GPU, sharing an NCCL communicator.
+ * per GPU, sharing an NCCL communicator.  --halo 1 switches the slab exchange from NCCL send/recv to
+ * the fused direct-NVLink kernel (lbm_peer_export / lbm_peer_connect).
  *
  * Deviations from the reference's stdout, all deliberate:
  *   - "Threads used:" prints the GPU count;
@@ -34,7 +35,7 @@
 #include "lbm_b200.h"
 
 typedef struct {
-    int N, Re, SAVETXT, METHOD, DIAG, skip, gpus;
+    int N, Re, SAVETXT, METHOD, DIAG, skip, gpus, halo;
     double UMAX, THRESH, GAMMA, MAGIC, MAXITER;
 } options;
 
@@ -44,6 +45,7 @@ typedef struct {
     const unsigned char *nccl_id;
     pthread_barrier_t *bar;
     double *u1, *u2, *u3, *vmag; /* shared N^3 arrays (SAVETXT) */
+    unsigned char (*blobs)[LBM_PEER_BLOB_BYTES]; /* --halo 1: one export blob per rank */
     int status;
 } worker;
 
@@ -133,6 +135,13 @@ static void *run(void *arg) {
     if (rc) die_lbm(rc);
     lbm_info info;
     lbm_get_info(ctx, &info);
+    if (o->halo == 1 && o->gpus > 1) { /* fused direct-NVLink halo instead of NCCL send/recv */
+        if ((rc = lbm_peer_export(ctx, w->blobs[w->rank]))) die_lbm(rc);
+        pthread_barrier_wait(w->bar);
+        if ((rc = lbm_peer_connect(ctx, w->rank > 0 ? w->blobs[w->rank - 1] : NULL,
+                                   w->rank + 1 < o->gpus ? w->blobs[w->rank + 1] : NULL))) die_lbm(rc);
+        pthread_barrier_wait(w->bar);
+    }
 
     if (root) { /* 3D:80-88 */
         printf("Re =\t%d\n", o->Re);
@@ -206,7 +215,7 @@ static int flag(int argc, char **argv, int *i, const char *name, const char **va
 
 int main(int argc, char **argv) {
     /* defaults = the reference's #defines, 3D:7-15, 18, 22, 43 */
-    options o = {.N = 50, .Re = 100, .SAVETXT = 1, .METHOD = 1, .DIAG = 0, .skip = 500, .gpus = 1,
+    options o = {.N = 50, .Re = 100, .SAVETXT = 1, .METHOD = 1, .DIAG = 0, .skip = 500, .gpus = 1, .halo = 0,
                  .UMAX = 0.1, .THRESH = 1E-12, .GAMMA = 1.0, .MAGIC = 0.25, .MAXITER = 1E8};
     for (int i = 1; i < argc; i++) {
         const char *v;
@@ -222,6 +231,7 @@ int main(int argc, char **argv) {
         else if (flag(argc, argv, &i, "--MAXITER", &v)) o.MAXITER = atof(v);
         else if (flag(argc, argv, &i, "--skip", &v)) o.skip = atoi(v);
         else if (flag(argc, argv, &i, "--gpus", &v) || flag(argc, argv, &i, "--THREADS", &v)) o.gpus = atoi(v);
+        else if (flag(argc, argv, &i, "--halo", &v)) o.halo = atoi(v);
         else {
             fprintf(stderr, "unknown argument %s\n", argv[i]);
             return 2;
@@ -249,15 +259,16 @@ int main(int argc, char **argv) {
     }
     pthread_barrier_t bar;
     pthread_barrier_init(&bar, NULL, (unsigned)o.gpus);
+    unsigned char(*blobs)[LBM_PEER_BLOB_BYTES] = calloc((size_t)o.gpus, LBM_PEER_BLOB_BYTES);
     worker *ws = calloc((size_t)o.gpus, sizeof(worker));
     pthread_t *th = calloc((size_t)o.gpus, sizeof(pthread_t));
     for (int r = 0; r < o.gpus; r++) {
         ws[r] = (worker){.rank = r, .opt = &o, .nccl_id = id, .bar = &bar, .u1 = u1, .u2 = u2, .u3 = u3,
-                         .vmag = vmag, .status = 1};
+                         .vmag = vmag, .blobs = blobs, .status = 1};
         if (r > 0) pthread_create(&th[r], NULL, run, &ws[r]);
     }
     run(&ws[0]);
     for (int r = 1; r < o.gpus; r++) pthread_join(th[r], NULL);
-    free(u1); free(u2); free(u3); free(vmag); free(ws); free(th);
+    free(u1); free(u2); free(u3); free(vmag); free(ws); free(th); free(blobs);
     return 0;
 }

@@ -79,3 +79,22 @@ def test_default_configuration_drop_in(tmp_path):
         data = np.loadtxt(fh, delimiter=",")
     for col, name in ((3, "u"), (4, "v"), (5, "w"), (6, "vmag")):
         assert np.array_equal(np.round(data[:, col] * 1e10).astype(np.int32), g[name + "_e10"]), name
+
+
+def test_lbm3d_cavity_multi_gpu_matches_single_gpu(tmp_path):
+    """`--gpus 2` (one host thread per GPU, NCCL halo) and `--gpus 2 --halo 1` (fused direct-NVLink
+    halo, same-process peer access) must write the same Solution_*.dat as one GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    outs = []
+    for extra in ([], ["--gpus", "2"], ["--gpus", "2", "--halo", "1"]):
+        d = tmp_path / ("run%d" % len(outs))
+        d.mkdir()
+        r = subprocess.run([EXE3, "--N", "30", "--Re", "60", "--THRESH", "1e-6"] + extra, cwd=d, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+        its = re.findall(r"\nIteration (\d+):\ndf/df0:\t(\S+)\n", r.stdout)
+        outs.append((its, open(d / "Solution_n=30Re=60_DIAG=0_2RT_M=0.250.dat").read()))
+    assert outs[0][0] == outs[1][0] == outs[2][0] and len(outs[0][0]) >= 2
+    assert outs[0][1] == outs[1][1] == outs[2][1]

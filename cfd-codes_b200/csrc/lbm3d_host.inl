@@ -1,0 +1,313 @@
+// lbm3d_host.inl -- host side of the D3Q19 path: launch geometry, kernel-parameter set-up, the
+// per-iteration stream/event schedule (single GPU, NCCL halo, fused direct halo), CUDA-graph replay,
+// materialisation of the reference's f2.  Included by lbm_b200.cu after lbm_ctx.h.
+static void choose_block(const lbm_ctx *c, dim3 *blk, dim3 *grd_xy) {
+    int bx = c->block_x, by = c->block_y;
+    // 128-thread blocks measured best on B200 (profiles/): 4-5 blocks per SM at <= 128 registers.
+    if (bx <= 0) {
+        bx = ((c->N + 31) / 32) * 32;
+        if (bx > 128) bx = 128;
+        // prefer a divisor of the row so that no lanes idle (N = 512 -> 128, N = 320 -> 64)
+        if (c->N > 128) {
+            for (int cand = 128; cand >= 64; cand -= 32)
+                if (c->N % cand == 0) { bx = cand; break; }
+        }
+    }
+    if (by <= 0) {
+        by = 128 / bx;
+        if (by < 1) by = 1;
+        if (by > c->N) by = c->N;
+    }
+    *blk = dim3(bx, by, 1);
+    *grd_xy = dim3((c->N + bx - 1) / bx, (c->N + by - 1) / by, 1);
+}
+
+// velocities 3D:36-38
+static const int CX19[19] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 0, 0, 1, -1, 1, -1, 0, 0};
+static const int CY19[19] = {0, 0, 0, 1, -1, 0, 0, 1, -1, 0, 0, 1, -1, -1, 1, 0, 0, 1, -1};
+static const int CZ19[19] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 0, 0, -1, 1, -1, 1};
+
+static void kp_set_lattices(const lbm_ctx *c, lbm3d::KP *p, const double *src, double *dst) {
+    for (int q = 0; q < lbm3d::Q; q++) {
+        const long long shift = (long long)CX19[q] + (long long)CY19[q] * c->N + (long long)CZ19[q] * c->N2;
+        p->srcq[q] = src ? src + (long long)q * c->PS - shift : nullptr;
+        p->dstq[q] = dst ? dst + (long long)q * c->PS : nullptr;
+    }
+}
+
+static lbm3d::KP make_kp(const lbm_ctx *c) {
+    lbm3d::KP p;
+    memset(&p, 0, sizeof(p));
+    p.N = c->N; p.M = c->N - 1; p.Mz = c->N - 1;
+    p.nzl = c->nzl; p.k0 = c->k0;
+    p.kl0 = 0; p.kstride = 1; p.partial_base = 0;
+    p.N2 = c->N2; p.PS = c->PS; p.FS = c->FS;
+    p.omega = c->OMEGA; p.omegam = c->OMEGAm; p.omomega = c->OmOMEGA; p.gammainv = c->gammainv;
+    p.ulid = c->ulid; p.vlid = c->vlid; p.wlid = c->wlid;
+    p.vfrac = 1.0 / (c->vlid + 1.0);  // 3D:386
+    p.third = 1.0 / 3.0;              // 3D:42
+    p.sixth = 1.0 / 6.0;              // 3D:41
+    p.flag = c->d_flag;
+    p.partials = c->partials;
+    p.Fbuf = c->Fbuf;
+    return p;
+}
+
+struct PeerBlob {   // what lbm_peer_export hands to the neighbours (<= LBM_PEER_BLOB_BYTES)
+    int magic, pid, dev, nzl;
+    long long PS, pad;
+    cudaIpcMemHandle_t lat[2], sig;
+    void *raw_lat[2], *raw_sig;
+};
+static_assert(sizeof(PeerBlob) <= LBM_PEER_BLOB_BYTES, "PeerBlob too large");
+
+template <int MODE>
+static void launch_step_peer(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, dim3 blk, cudaStream_t st) {
+    const bool g1 = (c->prm.GAMMA == 1.0);
+    if (c->prm.METHOD == 1) {
+        if (g1) lbm3d::k_step<1, MODE, true, true><<<grid, blk, 0, st>>>(p);
+        else    lbm3d::k_step<1, MODE, false, true><<<grid, blk, 0, st>>>(p);
+    } else {
+        if (g1) lbm3d::k_step<0, MODE, true, true><<<grid, blk, 0, st>>>(p);
+        else    lbm3d::k_step<0, MODE, false, true><<<grid, blk, 0, st>>>(p);
+    }
+    c->launches++;
+}
+
+template <int MODE>
+static void launch_step_mode(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, dim3 blk, cudaStream_t st) {
+    const bool g1 = (c->prm.GAMMA == 1.0);  // x * (1.0 / 1.0) == x: the specialised kernel drops the multiply
+    if (c->prm.METHOD == 1) {
+        if (g1) lbm3d::k_step<1, MODE, true><<<grid, blk, 0, st>>>(p);
+        else    lbm3d::k_step<1, MODE, false><<<grid, blk, 0, st>>>(p);
+    } else {
+        if (g1) lbm3d::k_step<0, MODE, true><<<grid, blk, 0, st>>>(p);
+        else    lbm3d::k_step<0, MODE, false><<<grid, blk, 0, st>>>(p);
+    }
+    c->launches++;
+}
+
+static void launch_step(lbm_ctx *c, int mode, const lbm3d::KP &p, dim3 grid, dim3 blk, cudaStream_t st) {
+    if (mode == lbm3d::MODE_STEP && c->vec2 && (c->N % 2) == 0) {
+        const bool g1 = (c->prm.GAMMA == 1.0);
+        dim3 g2((c->N / 2 + blk.x - 1) / blk.x, grid.y, grid.z);
+        if (c->prm.METHOD == 1) {
+            if (g1) lbm3d::k_step_x2<1, true><<<g2, blk, 0, st>>>(p);
+            else    lbm3d::k_step_x2<1, false><<<g2, blk, 0, st>>>(p);
+        } else {
+            if (g1) lbm3d::k_step_x2<0, true><<<g2, blk, 0, st>>>(p);
+            else    lbm3d::k_step_x2<0, false><<<g2, blk, 0, st>>>(p);
+        }
+        c->launches++;
+        return;
+    }
+    switch (mode) {
+        case lbm3d::MODE_STEP: launch_step_mode<lbm3d::MODE_STEP>(c, p, grid, blk, st); break;
+        case lbm3d::MODE_STEP_STOREF: launch_step_mode<lbm3d::MODE_STEP_STOREF>(c, p, grid, blk, st); break;
+        case lbm3d::MODE_STEP_DIFF_STOREF: launch_step_mode<lbm3d::MODE_STEP_DIFF_STOREF>(c, p, grid, blk, st); break;
+        default: launch_step_mode<lbm3d::MODE_MATERIALISE>(c, p, grid, blk, st); break;
+    }
+}
+
+static long long blocks_per_plane(const lbm_ctx *c) {
+    dim3 blk, g;
+    choose_block(c, &blk, &g);
+    return (long long)g.x * g.y;
+}
+
+static int ensure_Fbuf(lbm_ctx *c) {
+    if (c->Fbuf) return LBM_OK;
+    int rc = dev_alloc(c, &c->Fbuf, (long long)lbm3d::Q * c->FS);
+    if (rc) return rc;
+    c->f_valid = false;
+    return LBM_OK;
+}
+
+static int ensure_partials(lbm_ctx *c) {
+    const long long need = blocks_per_plane(c) * c->nzl;
+    if (c->partials && c->npartials >= need) return LBM_OK;
+    if (c->partials) { cudaFree(c->partials); c->bytes -= c->npartials * 8; c->partials = nullptr; }
+    int rc = dev_alloc(c, &c->partials, need);
+    if (rc) return rc;
+    c->npartials = need;
+    return LBM_OK;
+}
+
+// Exchange the face-crossing populations of lattice `L` (just written) with the z-neighbours.
+// Up-going populations (cz=+1) of my top plane -> bottom ghost of rank+1; down-going (cz=-1) of my
+// bottom plane -> top ghost of rank-1.  Each is one contiguous N^2 block (z is the slowest axis, 3D:48).
+static int halo_exchange(lbm_ctx *c, double *L, cudaStream_t st) {
+    const int r = c->prm.rank, P = c->prm.nranks;
+    const size_t n = (size_t)c->N2;
+    NK(g_nccl.GroupStart());
+    for (int a = 0; a < 5; a++) {
+        if (r + 1 < P) {
+            NK(g_nccl.Send(L + (long long)Q_UP[a] * c->PS + (long long)c->nzl * c->N2, n, ncclDouble, r + 1, c->comm, st));
+            NK(g_nccl.Recv(L + (long long)Q_DN[a] * c->PS + (long long)(c->nzl + 1) * c->N2, n, ncclDouble, r + 1, c->comm, st));
+        }
+        if (r > 0) {
+            NK(g_nccl.Send(L + (long long)Q_DN[a] * c->PS + (long long)1 * c->N2, n, ncclDouble, r - 1, c->comm, st));
+            NK(g_nccl.Recv(L + (long long)Q_UP[a] * c->PS + (long long)0 * c->N2, n, ncclDouble, r - 1, c->comm, st));
+        }
+    }
+    NK(g_nccl.GroupEnd());
+    return LBM_OK;
+}
+
+static const int GRAPH_LEN = 60;
+
+static void drop_graphs(lbm_ctx *c) {
+    for (int k = 0; k < 6; k++)
+        if (c->graph_exec[k]) { cudaGraphExecDestroy(c->graph_exec[k]); c->graph_exec[k] = nullptr; }
+}
+
+static bool graphs_enabled(const lbm_ctx *c) {
+    if (c->prm.dim != 3 || c->prm.nranks != 1) return false;
+    if (c->graphs >= 0) return c->graphs != 0;
+    return c->FS <= (1LL << 21);   // auto: up to 128^3 cells the step is launch-latency-bound
+}
+
+static int run_iteration(lbm_ctx *c, int mode);
+
+// GRAPH_LEN plain iterations as one graph launch (captured on first use of each phase).
+static int run_graph_block(lbm_ctx *c) {
+    const int phase = (int)(c->steps % 3) * 2 + c->cur;
+    if (!c->graph_exec[phase]) {
+        const long long steps0 = c->steps, launches0 = c->launches;
+        const int cur0 = c->cur;
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(c->s_main, cudaStreamCaptureModeThreadLocal));
+        int rc = LBM_OK;
+        for (int k = 0; k < GRAPH_LEN && !rc; k++) rc = run_iteration(c, lbm3d::MODE_STEP);
+        cudaError_t e = cudaStreamEndCapture(c->s_main, &g);
+        c->steps = steps0; c->launches = launches0; c->cur = cur0;   // capturing executed nothing
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&c->graph_exec[phase], g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    }
+    CK(cudaGraphLaunch(c->graph_exec[phase], c->s_main));
+    c->steps += GRAPH_LEN;        // GRAPH_LEN is even and a multiple of 3: cur and the side slot phase are unchanged
+    c->launches += GRAPH_LEN;
+    c->f_valid = false;
+    c->residual_ready = false;
+    return LBM_OK;
+}
+
+// One iteration in the given mode.  Reads lat[cur], writes lat[cur^1] (unless MATERIALISE).
+static int run_iteration(lbm_ctx *c, int mode) {
+    dim3 blk, gxy;
+    choose_block(c, &blk, &gxy);
+    lbm3d::KP p = make_kp(c);
+    const bool real = (mode != lbm3d::MODE_MATERIALISE);
+    // iteration index t = c->steps (real step) or c->steps - 1 (re-materialising the last one)
+    const long long t = real ? c->steps : c->steps - 1;
+    const int src_i = real ? c->cur : (c->cur ^ 1);
+    kp_set_lattices(c, &p, c->lat[src_i], c->lat[src_i ^ 1]);
+    const long long side_n = (long long)c->nzl * c->N;
+    p.side_rd = c->side + ((t + 1) % 3) * side_n;  // written by iteration t-2
+    p.side_wr = c->side + (t % 3) * side_n;
+    const long long bpp = (long long)gxy.x * gxy.y;
+
+    const bool multi = c->prm.nranks > 1;
+    if (!multi || !real) {
+        if (multi && c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
+        p.kl0 = 0; p.kstride = 1; p.partial_base = 0;
+        launch_step(c, mode, p, dim3(gxy.x, gxy.y, c->nzl), blk, c->s_main);
+    } else {
+        // Two streams.  s_halo (high priority): the two slab-boundary planes, then the NCCL exchange
+        // of what they produced.  s_main: the interior planes, concurrently (the boundary launch is
+        // too small to fill the GPU on its own, and the exchange hides behind the interior).
+        //   interior(t) needs boundary(t-1): it reads planes 0 / nzl-1 of the source lattice and
+        //                overwrites planes 1 / nzl-2 of the lattice boundary(t-1) was reading;
+        //   boundary(t) needs interior(t-1) (same two reasons, mirrored) and exchange(t-1) (ghosts;
+        //                stream order on s_halo).
+        CK(cudaStreamWaitEvent(c->s_main, c->ev_bnd, 0));   // the record of iteration t-1 (no-op the first time)
+        CK(cudaEventRecord(c->ev_main, c->s_main));         // everything queued on s_main so far, incl. interior(t-1)
+        CK(cudaStreamWaitEvent(c->s_halo, c->ev_main, 0));
+        const int nb = c->nzl >= 2 ? 2 : 1;
+        p.kl0 = 0; p.kstride = c->nzl >= 2 ? c->nzl - 1 : 1; p.partial_base = 0;
+        if (!c->p2p) {
+            launch_step(c, mode, p, dim3(gxy.x, gxy.y, nb), blk, c->s_halo);
+            CK(cudaEventRecord(c->ev_bnd, c->s_halo));
+            int rc = halo_exchange(c, c->lat[src_i ^ 1], c->s_halo);
+            if (rc) return rc;
+        } else {
+            // Direct NVLink halo: wait until both neighbours finished their boundary kernels of the
+            // previous iteration (they filled my ghosts and are done reading the ghosts I overwrite
+            // now), then ONE kernel computes the boundary planes, stores the face-crossing
+            // populations into the neighbours' ghost planes and publishes this iteration's stamp.
+            const long long rel = t - c->p2p_base;
+            const int r = c->prm.rank, P = c->prm.nranks;
+            lbm3d::k_wait_arrivals<<<1, 1, 0, c->s_halo>>>(c->sig, r > 0 ? rel : 0, r + 1 < P ? rel : 0, c->d_flag,
+                                                            20000000000LL);
+            c->launches++;
+            const int dsti = src_i ^ 1;
+            for (int a = 0; a < 5; a++) {
+                p.peer_dn[a] = r > 0 ? c->peer_lat[0][dsti] + (long long)Q_DN[a] * c->peer_PS[0] + (long long)(c->peer_nzl[0] + 1) * c->N2
+                                     : nullptr;
+                p.peer_up[a] = r + 1 < P ? c->peer_lat[1][dsti] + (long long)Q_UP[a] * c->peer_PS[1] : nullptr;
+            }
+            p.done_count = c->done_count;
+            p.sig_dn = r > 0 ? c->peer_sig[0] + 1 : nullptr;      // I am the neighbour "above" rank-1
+            p.sig_up = r + 1 < P ? c->peer_sig[1] + 0 : nullptr;  // and the neighbour "below" rank+1
+            p.sig_value = rel + 1;
+            const dim3 grid(gxy.x, gxy.y, nb);
+            switch (mode) {
+                case lbm3d::MODE_STEP: launch_step_peer<lbm3d::MODE_STEP>(c, p, grid, blk, c->s_halo); break;
+                case lbm3d::MODE_STEP_STOREF: launch_step_peer<lbm3d::MODE_STEP_STOREF>(c, p, grid, blk, c->s_halo); break;
+                default: launch_step_peer<lbm3d::MODE_STEP_DIFF_STOREF>(c, p, grid, blk, c->s_halo); break;
+            }
+            CK(cudaEventRecord(c->ev_bnd, c->s_halo));
+        }
+        CK(cudaEventRecord(c->ev_halo, c->s_halo));
+        c->halo_pending = true;
+        if (c->nzl > 2) {
+            p.kl0 = 1; p.kstride = 1; p.partial_base = (int)(bpp * nb);
+            launch_step(c, mode, p, dim3(gxy.x, gxy.y, c->nzl - 2), blk, c->s_main);
+        }
+        if (mode == lbm3d::MODE_STEP_DIFF_STOREF) CK(cudaStreamWaitEvent(c->s_main, c->ev_bnd, 0));  // its block partials
+    }
+    CK(cudaGetLastError());
+    if (real) {
+        c->cur ^= 1;
+        c->steps++;
+        c->f_valid = (mode != lbm3d::MODE_STEP);
+        c->residual_ready = false;
+        if (mode == lbm3d::MODE_STEP_DIFF_STOREF) {
+            lbm3d::k_sum_partials<<<1, 1024, 0, c->s_main>>>(c->partials, bpp * c->nzl, c->d_red);
+            c->launches++;
+            CK(cudaGetLastError());
+            c->residual_ready = true;
+        }
+    } else {
+        c->f_valid = true;
+    }
+    return LBM_OK;
+}
+
+// Make Fbuf hold the reference's f2 of the latest iteration.
+static int materialise_F(lbm_ctx *c) {
+    int rc = ensure_Fbuf(c);
+    if (rc) return rc;
+    if (c->f_valid) return LBM_OK;
+    if (c->steps == 0) {
+        const long long n = c->FS;
+        lbm3d::k_fill_w<<<(unsigned)((n + 255) / 256), 256, 0, c->s_main>>>(c->Fbuf, c->FS);
+        c->launches++;
+        CK(cudaGetLastError());
+        c->f_valid = true;
+        return LBM_OK;
+    }
+    rc = run_iteration(c, lbm3d::MODE_MATERIALISE);
+    if (rc) return rc;
+    if (c->p2p) {
+        // With the direct halo a neighbour may already be one iteration ahead and would overwrite the
+        // ghost planes this kernel reads; a collective point after it keeps everybody behind it
+        // (so lbm_get_f / lbm_macrovars on a stale F buffer are collective calls in this mode).
+        NK(g_nccl.AllReduce(c->d_red + 1, c->d_red + 1, 1, ncclDouble, ncclSum, c->comm, c->s_main));
+    }
+    return LBM_OK;
+}
+

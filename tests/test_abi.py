@@ -92,7 +92,7 @@ def test_product_does_not_reference_the_oracle():
     pkg = os.path.join(ROOT, "cfd-codes_b200")
     for dirpath, _, files in os.walk(pkg):
         for fn in files:
-            if fn.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp")) or fn == "Makefile":
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".inl", ".c", ".cpp")) or fn == "Makefile":
                 txt = open(os.path.join(dirpath, fn), errors="ignore").read()
                 assert "oracle" not in txt.lower().replace("oracle/_ref", "").replace("the oracle", "") or fn.endswith(".md"), \
                     os.path.join(dirpath, fn)

@@ -13,6 +13,7 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/lbm_b200.h"

@@ -35,7 +35,10 @@ struct NcclApi {
 };
 static NcclApi g_nccl;
 
+static std::mutex g_nccl_mutex;  // host programs create one context per thread concurrently
+
 static int nccl_load() {
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
     if (g_nccl.h) return LBM_OK;
     const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
     void *h = nullptr;

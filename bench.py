@@ -128,7 +128,7 @@ def run_reference_arm(a, world, rank):
     line = {
         "impl": "reference", "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": sec / a.steps * 1e3, "higher_is_better": True,
-        "scaling": "strong" if a.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "3D lid-driven cavity D3Q19 %d^3 fp64 Re=%d TRT (reference CPU implementation)" % (N, a.Re),
                    "grid": N, "Re": a.Re, "method": "TRT", "iterations_per_step": iters},
         "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": threads, "kind": kind, "sample": sample},
@@ -362,14 +362,17 @@ def main():
     if rank == 0:
         line = {
             "metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "3D lid-driven cavity D3Q19 %d^3 fp64 Re=%d TRT%s" % (
                            N, a.Re, "" if world == 1 else ", z-slabs over %d GPUs" % world),
                        "grid": N, "Re": a.Re, "UMAX": 0.1, "method": "TRT", "iterations_per_step": block,
                        "step": "one residual block of the reference loop: %d iterations + diff" % block,
                        "l2": "inputs larger than L2: %.2f GB lattice per GPU vs 126 MB" % (19 * 8 * cells / world / 1e9),
-                       "parallelism": "z-slab x%d" % world, "halo": a.halo if world > 1 else None, "residual_last": res},
+                       "parallelism": "z-slab x%d" % world, "halo": a.halo if world > 1 else None, "residual_last": res,
+                       "scaling_note": "N=1 runs BASELINE configs[1] (256^3); N>1 strong-scale configs[2] (512^3) over z-slabs; "
+                                       "MLUPS is normalised per cell update (one GPU: 21.1 GLUPS at 256^3, 21.3 at 512^3, "
+                                       "profiles/r01_summary.md); use --grid 512 at N=1 for the strict strong-scaling base"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "wall_s_timed_region": t_wall,
         }

@@ -19,6 +19,7 @@ def ngpus():
 @pytest.mark.parametrize("world,args", [(2, ["--N", "32", "--steps", "40"]), (2, ["--N", "21", "--Re", "400", "--steps", "30"]),
                                         (2, ["--N", "16", "--method", "0", "--Re", "20", "--diag", "1", "--steps", "25"]),
                                         (4, ["--N", "30", "--steps", "30"]), (8, ["--N", "40", "--steps", "24"]),
+                                        (2, ["--N", "256", "--Re", "1000", "--steps", "6"]),     # BASELINE config 2 grid, 2 slabs
                                         (2, ["--halo", "p2p", "--N", "32", "--steps", "40"]),
                                         (2, ["--halo", "p2p", "--N", "21", "--Re", "400", "--steps", "30", "--track", "0"]),
                                         (4, ["--halo", "p2p", "--N", "30", "--steps", "30", "--diag", "1"]),

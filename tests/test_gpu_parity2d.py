@@ -63,6 +63,22 @@ def test_steady_state_matches_the_reference_program(lbm):
     assert np.allclose(u[297:300, 50], [0.08339286, 0.09005163, 0.09670737], atol=1e-8)
 
 
+def test_short_horizon_parity_at_config5_size(lbm, oracle):
+    """8192^2 (BASELINE config 5), Re = 10000: 3 iterations against the synchronous oracle, bit-exact
+    (compared through u, v, rho and the residual to keep host traffic small)."""
+    cfg = dict(N=8192, M=8192, Re=10000.0)
+    o = oracle.Oracle2D(scheme="sync", **cfg)
+    o.step(3)
+    r_o = o.residual()
+    mo = o.macro()
+    with lbm.Cavity2D(**cfg) as sim:
+        sim.step(3)
+        assert sim.residual() == pytest.approx(r_o, rel=1e-12)
+        mg = sim.macro()
+    for k in ("u", "v", "rho"):
+        assert np.array_equal(bits(mg[k]), bits(mo[k])), k
+
+
 def test_large_grid_properties(lbm):
     """8192^2 (BASELINE config 5), Re = 10000 (tau = 0.746): batching-invariance and symmetry-free
     sanity (finite, rho deviation small, lid row moving)."""

@@ -139,6 +139,23 @@ def run_reference_arm(a, world, rank):
     return 0
 
 
+def parity_probe(lbm, device):
+    """Not a measurement: a 2-second sanity probe so that every bench line carries its own evidence
+    that the timed library computes the reference's bits -- 12^3 TRT cavity, 10 iterations, sha256
+    of the raw distributions against the hash recorded from the REAL reference
+    (tests/golden/ref_hashes.json, made by tests/golden/make_golden.py from oracle/_ref)."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "ref_hashes.json")) as fh:
+            want = json.load(fh)["N12_Re100_m1_g1.0_d0_u0.1"]["10"]["sha256"]
+        with lbm.Cavity3D(N=12, Re=100, device=device) as sim:
+            sim.step(10)
+            got = hashlib.sha256(sim.f().tobytes()).hexdigest()
+        return {"case": "12^3 Re=100 TRT, 10 iterations", "sha256_equals_reference": got == want}
+    except Exception as e:
+        return {"case": "12^3 Re=100 TRT, 10 iterations", "error": repr(e)}
+
+
 def run_d2q9(a):
     """BASELINE config 5: 2D lid-driven cavity, D2Q9, 8192^2 fp64 on one B200 (144 B per cell update)."""
     from lbmpkg import lbm
@@ -355,6 +372,8 @@ def main():
                "call": "lbm_set_f(host) + lbm_step(%d) + lbm_residual + lbm_macrovars(host)" % block}
     sim.close()
 
+    parity = parity_probe(lbm, local_rank) if rank == 0 else None
+
     # ---- CPU baseline (rank 0, N=1 only): the reference's own main.c on this box's cores ---------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -380,7 +399,7 @@ def main():
                                        "MLUPS is normalised per cell update (one GPU: 21.1 GLUPS at 256^3, 21.3 at 512^3, "
                                        "profiles/r01_summary.md); use --grid 512 at N=1 for the strict strong-scaling base"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "wall_s_timed_region": t_wall,
+            "wall_s_timed_region": t_wall, "parity_probe": parity,
         }
         print(json.dumps(line), flush=True)
     if multi:

@@ -219,8 +219,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--block-x", type=int, default=0)
     ap.add_argument("--block-y", type=int, default=0)
-    ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"],
-                    help="multi-GPU halo transport: NCCL send/recv (default) or the fused direct NVLink stores")
+    ap.add_argument("--halo", default="auto", choices=["auto", "nccl", "p2p"],
+                    help="multi-GPU halo transport: NCCL send/recv, the fused direct-NVLink kernel (p2p), or auto = "
+                         "p2p below 2^21 cells per GPU (latency-bound slabs), NCCL above (profiles/r01_halo_p2p_vs_nccl.md)")
     ap.add_argument("--workload", default="cavity3d", choices=["cavity3d", "d2q9"],
                     help="d2q9: BASELINE config 5 (8192^2 D2Q9 variant of the kernel, 1 GPU; extra line, not the headline)")
     a = ap.parse_args()
@@ -278,6 +279,8 @@ def main():
     N = a.grid or (256 if world == 1 else 512)
     sim = lbm.Cavity3D(N=N, Re=a.Re, UMAX=0.1, METHOD=1, rank=rank, nranks=world, device=local_rank,
                        track_residual=True, nccl_id=nccl_id)
+    if a.halo == "auto":
+        a.halo = "p2p" if (multi and float(N) ** 3 / world < 2 ** 21) else "nccl"
     if multi and a.halo == "p2p":
         import cfd_codes_b200.distributed as D
         if not dist.is_initialized():

@@ -17,6 +17,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "d3q19_rules.h"
 
@@ -116,8 +117,21 @@ __device__ __forceinline__ void lbm_store(double *p, double v) {
 // checkfeq (feq < 0.0, 3D:688) is evaluated on the sign bits: the OR of the high words is
 // negative iff some feq has its sign bit set (feq = -0.0 cannot occur for finite rho != 0).
 // G1: GAMMA == 1.0 (the reference default): x * gammainv == x exactly, so the multiply is dropped.
+// (collide and apply_boundary are __host__ __device__ only so that tests/host_device_functions_check.cu
+//  can run the very same source on the CPU against the oracle; the library itself exports no host
+//  compute path.)
+__host__ __device__ __forceinline__ int lbm_hi32(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(x);
+#else
+    long long b;
+    memcpy(&b, &x, sizeof b);
+    return (int)(b >> 32);
+#endif
+}
+
 template <int METHOD, bool G1>
-__device__ __forceinline__ bool collide(double (&f)[Q], const KP &p) {
+__host__ __device__ __forceinline__ bool collide(double (&f)[Q], const KP &p) {
     // 3D:268-270 / 3D:225-235 (the += loop visits q = 0..18: same order, zero terms are exact)
     double rho = f[0] + f[1];
     rho += f[2]; rho += f[3]; rho += f[4]; rho += f[5]; rho += f[6]; rho += f[7]; rho += f[8];
@@ -147,7 +161,7 @@ __device__ __forceinline__ bool collide(double (&f)[Q], const KP &p) {
 
     {   // rest population, cdotu = 0: feq = w*rho*(1.0 + (0 - 1.5*U2)*gammainv)
         const double fe = wr0 * (1.0 + (G1 ? (-k15) : (-k15) * p.gammainv));
-        negbits |= __double2hiint(fe);
+        negbits |= lbm_hi32(fe);
         if (METHOD == 1) f[0] = f[0] - p.omega * (f[0] - fe);        // 3D:286
         else             f[0] = p.omomega * f[0] + p.omega * fe;     // 3D:246
     }
@@ -157,7 +171,7 @@ __device__ __forceinline__ bool collide(double (&f)[Q], const KP &p) {
         const double E = G1 ? (4.5 * (cc) - k15) : (4.5 * (cc) - k15) * p.gammainv;                  \
         const double fe1 = (wr) * ((1.0 + t3) + E);                                                  \
         const double fe2 = (wr) * ((1.0 - t3) + E);                                                  \
-        negbits |= __double2hiint(fe1) | __double2hiint(fe2);                                        \
+        negbits |= lbm_hi32(fe1) | lbm_hi32(fe2);                                             \
         if (METHOD == 1) { /* 3D:293-302 */                                                          \
             const double fplus = homega * ((f[q] + f[q + 1]) - (fe1 + fe2));                         \
             const double fminus = homegam * ((f[q] - f[q + 1]) - (fe1 - fe2));                       \
@@ -226,7 +240,7 @@ __device__ __forceinline__ bool collide(double (&f)[Q], const KP &p) {
         f[u5] = f[LBM_OPP(u5)];                             \
     } break;
 
-__device__ __forceinline__ void apply_boundary(double (&f)[Q], const int cls, const KP &p) {
+__host__ __device__ __forceinline__ void apply_boundary(double (&f)[Q], const int cls, const KP &p) {
     switch (cls) {
         LBM_D3Q19_FACES(LBM_FACE_CASE)
         case LBM_CLS(0, 2, 0): {  // the moving lid y = N-1, 3D:437-445

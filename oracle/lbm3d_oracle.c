@@ -124,7 +124,57 @@ void oracle3d_destroy(void *h) {
 
 static inline int inside(int a, int n) { return a >= 0 && a < n; }
 
-/* macrocollideandstream, 3D:215-321 */
+/* The collision of one cell, 3D:224-246 (BGK) / 3D:268-302 (TRT): f[19] (the reference's f1[x][:]) ->
+ * fs[19] (the values macrocollideandstream pushes to the neighbours; fs[0] stays local). */
+static inline void collide_cell(const oracle3d *o, const double *f, double *fs, int *neg) {
+    if (o->p.METHOD == 0) {
+        double rho = 0.0, u = 0.0, v = 0.0, w = 0.0;
+        for (int q = 0; q < Q; q++) {
+            double ft = f[q];
+            rho += ft;
+            u += CX[q] * ft;
+            v += CY[q] * ft;
+            w += CZ[q] * ft;
+        }
+        u /= rho; v /= rho; w /= rho;
+        double U2 = (u * u) + (v * v) + (w * w);
+        for (int q = 0; q < Q; q++) {
+            double feq = calcfeq(o, CX[q], CY[q], CZ[q], o->w[q], u, v, w, rho, U2, neg);
+            fs[q] = o->OmOMEGA * f[q] + o->OMEGA * feq;
+        }
+    } else {
+        double rho = f[0] + f[1] + f[2] + f[3] + f[4] + f[5] + f[6] + f[7] + f[8] + f[9] +
+                     f[10] + f[11] + f[12] + f[13] + f[14] + f[15] + f[16] + f[17] + f[18];
+        double rinv = 1.0 / rho;
+        double u = (CX[1] * f[1] + CX[2] * f[2] + CX[7] * f[7] + CX[8] * f[8] + CX[9] * f[9] +
+                    CX[10] * f[10] + CX[13] * f[13] + CX[14] * f[14] + CX[15] * f[15] +
+                    CX[16] * f[16]) * rinv;
+        double v = (CY[3] * f[3] + CY[4] * f[4] + CY[7] * f[7] + CY[8] * f[8] + CY[11] * f[11] +
+                    CY[12] * f[12] + CY[13] * f[13] + CY[14] * f[14] + CY[17] * f[17] +
+                    CY[18] * f[18]) * rinv;
+        double w = (CZ[5] * f[5] + CZ[6] * f[6] + CZ[9] * f[9] + CZ[10] * f[10] + CZ[11] * f[11] +
+                    CZ[12] * f[12] + CZ[15] * f[15] + CZ[16] * f[16] + CZ[17] * f[17] +
+                    CZ[18] * f[18]) * rinv;
+        double U2 = (u * u) + (v * v) + (w * w);
+        fs[0] = f[0] - o->OMEGA * (f[0] - calcfeq(o, 0, 0, 0, o->w[0], u, v, w, rho, U2, neg));
+        for (int q = 1; q < Q; q += 2) {
+            int op = q + 1;
+            double feq1 = calcfeq(o, CX[q], CY[q], CZ[q], o->w[q], u, v, w, rho, U2, neg);
+            double feq2 = calcfeq(o, CX[op], CY[op], CZ[op], o->w[op], u, v, w, rho, U2, neg);
+            double fplus = 0.5 * (f[q] + f[op]);
+            double fminus = 0.5 * (f[q] - f[op]);
+            double feqplus = 0.5 * (feq1 + feq2);
+            double feqminus = 0.5 * (feq1 - feq2);
+            fplus = o->OMEGA * (fplus - feqplus);
+            fminus = o->OMEGAm * (fminus - feqminus);
+            fs[q] = f[q] - fplus - fminus;
+            fs[op] = f[op] - fplus + fminus;
+        }
+    }
+}
+
+/* macrocollideandstream, 3D:215-321: collide, then push to x + c_q where that is inside the box
+ * (3D:252, 308, 314); the rest population is written locally (3D:286 / q = 0 in 3D:249-253). */
 static void collide_and_stream(oracle3d *o) {
     const int N = o->p.N;
     const double *f1 = o->f1;
@@ -134,64 +184,13 @@ static void collide_and_stream(oracle3d *o) {
     for (int k = 0; k < N; k++) {
         for (int j = 0; j < N; j++) {
             for (int i = 0; i < N; i++) {
-                double f[Q];
+                double f[Q], fs[Q];
                 int neg = 0;
                 for (int q = 0; q < Q; q++) f[q] = f1[LU4(o, i, j, k, q)];
-                if (o->p.METHOD == 0) {
-                    /* BGK, 3D:224-254 */
-                    double rho = 0.0, u = 0.0, v = 0.0, w = 0.0;
-                    for (int q = 0; q < Q; q++) {
-                        double ft = f[q];
-                        rho += ft;
-                        u += CX[q] * ft;
-                        v += CY[q] * ft;
-                        w += CZ[q] * ft;
-                    }
-                    u /= rho; v /= rho; w /= rho;
-                    double U2 = (u * u) + (v * v) + (w * w);
-                    for (int q = 0; q < Q; q++) {
-                        double feq = calcfeq(o, CX[q], CY[q], CZ[q], o->w[q], u, v, w, rho, U2, &neg);
-                        double fs = o->OmOMEGA * f[q] + o->OMEGA * feq;
-                        int in = i + CX[q], jn = j + CY[q], kn = k + CZ[q];
-                        if (inside(in, N) && inside(jn, N) && inside(kn, N))
-                            f2[LU4(o, in, jn, kn, q)] = fs;
-                    }
-                } else {
-                    /* TRT, 3D:268-316 */
-                    double rho = f[0] + f[1] + f[2] + f[3] + f[4] + f[5] + f[6] + f[7] + f[8] + f[9] +
-                                 f[10] + f[11] + f[12] + f[13] + f[14] + f[15] + f[16] + f[17] + f[18];
-                    double rinv = 1.0 / rho;
-                    double u = (CX[1] * f[1] + CX[2] * f[2] + CX[7] * f[7] + CX[8] * f[8] + CX[9] * f[9] +
-                                CX[10] * f[10] + CX[13] * f[13] + CX[14] * f[14] + CX[15] * f[15] +
-                                CX[16] * f[16]) * rinv;
-                    double v = (CY[3] * f[3] + CY[4] * f[4] + CY[7] * f[7] + CY[8] * f[8] + CY[11] * f[11] +
-                                CY[12] * f[12] + CY[13] * f[13] + CY[14] * f[14] + CY[17] * f[17] +
-                                CY[18] * f[18]) * rinv;
-                    double w = (CZ[5] * f[5] + CZ[6] * f[6] + CZ[9] * f[9] + CZ[10] * f[10] + CZ[11] * f[11] +
-                                CZ[12] * f[12] + CZ[15] * f[15] + CZ[16] * f[16] + CZ[17] * f[17] +
-                                CZ[18] * f[18]) * rinv;
-                    double U2 = (u * u) + (v * v) + (w * w);
-                    f2[LU4(o, i, j, k, 0)] =
-                        f[0] - o->OMEGA * (f[0] - calcfeq(o, 0, 0, 0, o->w[0], u, v, w, rho, U2, &neg));
-                    for (int q = 1; q < Q; q += 2) {
-                        int op = q + 1;
-                        double feq1 = calcfeq(o, CX[q], CY[q], CZ[q], o->w[q], u, v, w, rho, U2, &neg);
-                        double feq2 = calcfeq(o, CX[op], CY[op], CZ[op], o->w[op], u, v, w, rho, U2, &neg);
-                        double fplus = 0.5 * (f[q] + f[op]);
-                        double fminus = 0.5 * (f[q] - f[op]);
-                        double feqplus = 0.5 * (feq1 + feq2);
-                        double feqminus = 0.5 * (feq1 - feq2);
-                        fplus = o->OMEGA * (fplus - feqplus);
-                        fminus = o->OMEGAm * (fminus - feqminus);
-                        double fs1 = f[q] - fplus - fminus;
-                        double fs2 = f[op] - fplus + fminus;
-                        int in = i + CX[q], jn = j + CY[q], kn = k + CZ[q];
-                        if (inside(in, N) && inside(jn, N) && inside(kn, N))
-                            f2[LU4(o, in, jn, kn, q)] = fs1;
-                        in = i + CX[op]; jn = j + CY[op]; kn = k + CZ[op];
-                        if (inside(in, N) && inside(jn, N) && inside(kn, N))
-                            f2[LU4(o, in, jn, kn, op)] = fs2;
-                    }
+                collide_cell(o, f, fs, &neg);
+                for (int q = 0; q < Q; q++) {
+                    int in = i + CX[q], jn = j + CY[q], kn = k + CZ[q];
+                    if (inside(in, N) && inside(jn, N) && inside(kn, N)) f2[LU4(o, in, jn, kn, q)] = fs[q];
                 }
                 neg_any |= neg;
             }
@@ -419,4 +418,41 @@ double oracle3d_time_steps(void *h, int n, int nthreads) {
     oracle3d_step(h, n, nthreads, 0);
     return 0.0;
 #endif
+}
+
+/* ---- single-cell entry points for tests of the product's device functions compiled for the host
+ *      (tests/host_device_functions_check.cu) ------------------------------------------------------ */
+int oracle3d_collide_cell(void *h, const double *f19, double *out19) {
+    int neg = 0;
+    collide_cell((const oracle3d *)h, f19, out19, &neg);
+    return neg;
+}
+
+/* HechtBC rule of the boundary class (bx, by, bz) in {0: inside, 1: coordinate 0, 2: coordinate N-1}
+ * applied in place to ONE cell's 19 populations.  Returns 0 if the class has no rule (interior). */
+int oracle3d_rule_cell(void *h, int bx, int by, int bz, double *f19) {
+    oracle3d tmp = *(const oracle3d *)h;
+    tmp.N3 = 1; /* population stride of a single cell */
+    const int nb = (bx != 0) + (by != 0) + (bz != 0);
+    if (nb == 0) return 0;
+    if (nb == 1) {
+        if (bz == 1) apply_face(&tmp, f19, 0, &FACE_Z0);
+        else if (bz == 2) apply_face(&tmp, f19, 0, &FACE_ZM);
+        else if (bx == 1) apply_face(&tmp, f19, 0, &FACE_X0);
+        else if (bx == 2) apply_face(&tmp, f19, 0, &FACE_XM);
+        else if (by == 1) apply_face(&tmp, f19, 0, &FACE_Y0);
+        else apply_lid(&tmp, f19, 0, 1.0 / (tmp.vlid + 1.0));
+        return 1;
+    }
+    if (nb == 2) {
+        for (int e = 0; e < 12; e++)
+            if (EDGES[e].bx == bx && EDGES[e].by == by && EDGES[e].bz == bz) { apply_edge(&tmp, f19, 0, &EDGES[e]); return 2; }
+        return -1;
+    }
+    for (int c = 0; c < 8; c++)
+        if (CORNERS[c].bx == bx && CORNERS[c].by == by && CORNERS[c].bz == bz) {
+            for (int a = 0; a < 6; a++) f19[CORNERS[c].u[a]] = f19[opp(CORNERS[c].u[a])];
+            return 3;
+        }
+    return -1;
 }

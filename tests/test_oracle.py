@@ -125,3 +125,23 @@ def test_golden_file_n29(oracle):
         # every value equals the golden one at the 10 printed decimals (zero signs aside)
         assert np.array_equal(np.round(a, 10) + 0.0, np.round(g[name], 10) + 0.0), name
     assert np.array_equal(g["x"].reshape(N, N, N)[:, 0, 0], np.arange(N))
+
+
+def test_product_device_functions_compiled_for_host_match_oracle(oracle, tmp_path):
+    """The product's collide<METHOD, G1> and apply_boundary (csrc/lbm3d_kernels.cuh + d3q19_rules.h) are
+    `__host__ __device__`; tests/host_device_functions_check.cu compiles that same source for the CPU and
+    compares it bit-for-bit with the oracle's single-cell entry points: 26 boundary classes, BGK and
+    TRT, DIAG 0/1, GAMMA 1/0.5/2, including far-from-equilibrium cells (negative-feq flag)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "hdf_check")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-fmad=false", "-Xcompiler",
+                           "-ffp-contract=off", "-I", os.path.join(root, "cfd-codes_b200", "csrc"),
+                           os.path.join(root, "tests", "host_device_functions_check.cu"), "-L", os.path.join(root, "oracle"),
+                           "-llbm_oracle", "-Xlinker", "-rpath," + os.path.join(root, "oracle"), "-o", exe])
+    r = subprocess.run([exe, "8000"], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-800:]

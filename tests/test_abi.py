@@ -107,3 +107,26 @@ def test_fast_formatter_equals_printf(tmp_path):
                            os.path.join(ROOT, "tests", "fmt10_check.c"), "-lm"])
     r = subprocess.run([exe, "1500000"], capture_output=True, text=True)
     assert r.returncode == 0 and "fmt10 ok" in r.stdout, r.stdout[-500:]
+
+
+def test_step_kernel_resource_budget(lbm):
+    """Performance invariants of the dominant kernel that can be checked without a GPU: the TRT step
+    kernel must fit 5 blocks of 128 threads per SM (<= 102 registers, profiles/r01_ab_occupancy.log),
+    must not spill (no local-memory stack), and uses no shared memory."""
+    out = subprocess.run(["cuobjdump", "-res-usage", lbm.LIB_PATH], capture_output=True, text=True).stdout
+    m = re.search(r"Function _ZN5lbm3d6k_stepILi1ELi0ELb1ELb0EEEvNS_2KPE:\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", out)
+    assert m, out[:500]
+    reg, stack, shared, local = (int(x) for x in m.groups())
+    assert reg <= 102 and stack == 0 and shared == 0 and local == 0, (reg, stack, shared, local)
+    # the D2Q9 kernel: 4 blocks of 256 threads per SM
+    m = re.search(r"Function _ZN5lbm2d7k2_stepENS_3KP2E:\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    assert m and int(m.group(1)) <= 64 and int(m.group(2)) == 0
+
+
+def test_step_kernel_memory_instructions(lbm):
+    """One load and one store per population and cell: exactly 19 LDG.E.64 on the fast path plus the
+    stale-f14 side load, 19 STG.E.64 plus the side store, and no 32-bit or local-memory traffic."""
+    out = subprocess.run(["cuobjdump", "-sass", lbm.LIB_PATH], capture_output=True, text=True).stdout
+    sec = [x for x in re.split(r"\n\s*Function : ", out) if x.startswith("_ZN5lbm3d6k_stepILi1ELi0ELb1ELb0EEEvNS_2KPE")][0]
+    assert len(re.findall(r"\bLDG\.E\.64\b", sec)) == 20 and len(re.findall(r"\bSTG\.E\.64\b", sec)) == 20
+    assert not re.findall(r"\b(LDL|STL)\b", sec)

@@ -97,18 +97,22 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def cpu_reference(N, Re, iters, warm, steps, threads):
+def cpu_reference(N, Re, iters, warm, steps, threads, seconds=None):
     """Time the reference's own CPU implementation of the path (oracle/_ref if it was compiled for
-    this grid, else the oracle port with 64-bit indexing).  Returns (mlups, kind, sample, seconds)."""
+    this grid, else the oracle port with 64-bit indexing).  `seconds`: run whole iterations until that
+    much wall time has passed instead of a fixed count.  Returns (mlups, kind, sample, seconds)."""
     from oracle import oracle as O
     cfg = dict(N=N, Re=Re)
     if O.ref_available(**cfg):
         exe = O.ref_binary(**cfg)
-        r = subprocess.run([exe, "bench", str(iters), str(warm), str(steps), str(threads)], capture_output=True,
-                           text=True, check=True)
+        if seconds:
+            cmd = [exe, "sample", str(seconds), str(warm), str(threads)]
+        else:
+            cmd = [exe, "bench", str(iters), str(warm), str(steps), str(threads)]
+        r = subprocess.run(cmd, capture_output=True, text=True, check=True)
         j = json.loads(r.stdout.strip().splitlines()[-1])
-        return j["mlups"], "reference", "%d+%d steps x %d iterations of the %d^3 grid, oracle/_ref (reference main.c)" % (
-            warm, steps, iters, N), j["seconds"]
+        return j["mlups"], "reference", "%d+%d iterations of the %d^3 grid (%.1f s), oracle/_ref (reference main.c)" % (
+            j["warmup"] * j["iters_per_step"], j["steps"] * j["iters_per_step"], N, j["seconds"]), j["seconds"]
     o = O.Oracle3D(N=N, Re=Re, threads=threads)
     if warm:
         o.step(warm * iters, want_diff=False)
@@ -382,7 +386,7 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
             thr = host_threads()
-            m, kind, sample, sec = cpu_reference(N, a.Re, 1, 1, 3, thr)
+            m, kind, sample, sec = cpu_reference(N, a.Re, 1, 1, 3, thr, seconds=12.0)   # a bounded ~12 s sample
             cpu = {"value": m, "unit": "MLUPS", "cores": thr, "kind": kind, "sample": sample, "seconds": sec}
         except Exception as e:  # the baseline must never take the bench line down
             cpu = {"value": None, "unit": "MLUPS", "cores": host_threads(), "kind": "port", "sample": "failed: %r" % (e,)}

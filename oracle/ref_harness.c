@@ -21,6 +21,10 @@
  *   bench <iters> <warm> <steps> [threads]
  *                                   `warm` untimed + `steps` timed bench steps of `iters`
  *                                   iterations each (bench.py --impl reference); JSON line.
+ *   sample <seconds> <warm> [threads]
+ *                                   `warm` untimed iterations, then whole iterations until at least
+ *                                   <seconds> of wall time have passed (>= 3): the bounded CPU
+ *                                   sample of bench.py's cpu_baseline; JSON line.
  *   main                            runs the reference's own main() (3D:74-132)
  *                                   in the current directory (banner, residual
  *                                   blocks, Solution_*.dat).
@@ -110,6 +114,33 @@ int main(int argc, char **argv) {
         printf("{\"N\": %d, \"iters_per_step\": %d, \"steps\": %d, \"warmup\": %d, \"seconds\": %.6f, "
                "\"mlups\": %.6f, \"threads\": %d}\n",
                N, iters, steps, warm, dt, cells * steps * iters / dt / 1e6, omp_get_max_threads());
+        return 0;
+    }
+    if (strcmp(argv[1], "sample") == 0 && argc >= 4) {
+        double want = atof(argv[2]);
+        int warm = atoi(argv[3]);
+        int nt = argc > 4 ? atoi(argv[4]) : 0;
+        allocate();
+        initialize();
+        set_threads(nt);
+        for (int t = 0; t < warm; t++) {
+            macrocollideandstream();
+            HechtBC(f2);
+            swap(&f1, &f2);
+        }
+        int n = 0;
+        double t0 = omp_get_wtime(), dt = 0.0;
+        while (n < 3 || dt < want) {
+            macrocollideandstream();
+            HechtBC(f2);
+            swap(&f1, &f2);
+            n++;
+            dt = omp_get_wtime() - t0;
+        }
+        double cells = (double)N * (double)N * (double)N;
+        printf("{\"N\": %d, \"iters_per_step\": 1, \"steps\": %d, \"warmup\": %d, \"seconds\": %.6f, "
+               "\"mlups\": %.6f, \"threads\": %d}\n",
+               N, n, warm, dt, cells * n / dt / 1e6, omp_get_max_threads());
         return 0;
     }
     fprintf(stderr, "bad arguments\n");

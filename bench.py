@@ -116,6 +116,13 @@ def cpu_reference(N, Re, iters, warm, steps, threads, seconds=None):
     o = O.Oracle3D(N=N, Re=Re, threads=threads)
     if warm:
         o.step(warm * iters, want_diff=False)
+    if seconds:
+        n, sec = 0, 0.0
+        while n < 3 or sec < seconds:
+            sec += o.time_steps(1)
+            n += 1
+        o.close()
+        return N ** 3 * n / sec / 1e6, "port", "%d+%d iterations of the %d^3 grid (%.1f s), oracle port" % (warm, n, N, sec), sec
     sec = o.time_steps(steps * iters)
     o.close()
     return N ** 3 * steps * iters / sec / 1e6, "port", "%d+%d steps x %d iterations of the %d^3 grid, oracle port" % (

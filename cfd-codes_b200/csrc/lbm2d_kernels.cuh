@@ -37,7 +37,7 @@ struct KP2 {
 };
 
 // TRT collision of one cell in the reference's operation order (2D:360-413), in place.
-__device__ __forceinline__ void collide(double (&ft)[Q], const KP2 &p) {
+__host__ __device__ __forceinline__ void collide(double (&ft)[Q], const KP2 &p) {  // host: tests only
     const double drho = ft[0] + ft[1] + ft[2] + ft[3] + ft[4] + ft[5] + ft[6] + ft[7] + ft[8];  // 2D:360-361
     const double ux = ft[1] + ft[5] + ft[8] - (ft[3] + ft[6] + ft[7]);                          // 2D:362
     const double uy = ft[2] + ft[5] + ft[6] - (ft[4] + ft[7] + ft[8]);                          // 2D:363

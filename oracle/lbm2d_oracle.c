@@ -5,7 +5,7 @@
  *   /root/reference/2D Lid-driven Cavity with Lattice Boltzmann Method/main.cpp   ("2D:")
  * streamCollide 2D:281-416, macroVars 2D:419-449, convergence 2D:452-478, constants 2D:12-31.
  *
- * TWO time-stepping schemes over the SAME cell arithmetic (function cell_update below):
+ * TWO time-stepping schemes over the SAME cell arithmetic (functions pull and collide below):
  *
  *  (A) oracle2d_*  "synchronous": two lattices, every cell reads step t and writes step t+1.
  *      This is what the GPU kernel computes and the GPU is tested bit-for-bit
@@ -347,4 +347,11 @@ void inplace2d_get_macro(void *h, double *u, double *v, double *rho) {
         memcpy(rho + off, r->rho, n * sizeof(double));
         off += n;
     }
+}
+
+/* single-cell entry point for tests/host_device_functions_check.cu */
+void oracle2d_collide_cell(const oracle2d_params *p, const double *ft9, double *out9) {
+    consts2d c;
+    derive(p, &c);
+    collide(&c, ft9, out9);
 }

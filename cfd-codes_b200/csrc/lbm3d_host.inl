@@ -1,6 +1,14 @@
 // lbm3d_host.inl -- host side of the D3Q19 path: launch geometry, kernel-parameter set-up, the
 // per-iteration stream/event schedule (single GPU, NCCL halo, fused direct halo), CUDA-graph replay,
 // materialisation of the reference's f2.  Included by lbm_b200.cu after lbm_ctx.h.
+// Stale-f14 history of the x = N-1 face: SIDE_DEPTH slots of [nzl][N]; iteration t writes slot
+// t % SIDE_DEPTH and reads the slot iteration t-2 wrote.  Depth 4 (not 3) so that the two fused
+// iterations of k_step_pair read {t+2, t+3} and write {t, t+1}: disjoint (lbm3d_pair.cuh).
+static const int SIDE_DEPTH = 4;
+static double *side_slot(const lbm_ctx *c, long long t) {
+    return c->side + (t % SIDE_DEPTH) * ((long long)c->nzl * c->N);
+}
+
 static void choose_block(const lbm_ctx *c, dim3 *blk, dim3 *grd_xy) {
     int bx = c->block_x, by = c->block_y;
     // 128-thread blocks measured best on B200 (profiles/): 4-5 blocks per SM at <= 128 registers.
@@ -41,6 +49,7 @@ static lbm3d::KP make_kp(const lbm_ctx *c) {
     p.N = c->N; p.M = c->N - 1; p.Mz = c->N - 1;
     p.nzl = c->nzl; p.k0 = c->k0;
     p.kl0 = 0; p.kstride = 1; p.partial_base = 0;
+    p.G = c->G; p.zlo = 0; p.zhi = c->nzl; p.Lz = c->nzl;
     p.N2 = c->N2; p.PS = c->PS; p.FS = c->FS;
     p.omega = c->OMEGA; p.omegam = c->OMEGAm; p.omomega = c->OmOMEGA; p.gammainv = c->gammainv;
     p.ulid = c->ulid; p.vlid = c->vlid; p.wlid = c->wlid;
@@ -109,6 +118,81 @@ static void launch_step(lbm_ctx *c, int mode, const lbm3d::KP &p, dim3 grid, dim
     }
 }
 
+// ---- two iterations per pass (lbm3d_pair.cuh) -------------------------------------------------------
+template <int TY, int MINB, bool PIPE>
+static int launch_pair_v(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, cudaStream_t st) {
+    const bool g1 = (c->prm.GAMMA == 1.0);
+    const dim3 blk(lbm3d::PAIR_TX, TY, 1);
+    const int smem = lbm3d::pair_smem_bytes(TY);
+#define LBM_PAIR_LAUNCH(M_, G_)                                                                              \
+    do {                                                                                                     \
+        static bool attr_done[16] = {false};                                                                 \
+        if (!attr_done[c->dev & 15]) {                                                                       \
+            CK(cudaFuncSetAttribute(lbm3d::k_step_pair<M_, G_, TY, MINB, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            attr_done[c->dev & 15] = true;                                                                   \
+        }                                                                                                    \
+        lbm3d::k_step_pair<M_, G_, TY, MINB, PIPE><<<grid, blk, smem, st>>>(p);                              \
+    } while (0)
+    if (c->prm.METHOD == 1) {
+        if (g1) LBM_PAIR_LAUNCH(1, true); else LBM_PAIR_LAUNCH(1, false);
+    } else {
+        if (g1) LBM_PAIR_LAUNCH(0, true); else LBM_PAIR_LAUNCH(0, false);
+    }
+#undef LBM_PAIR_LAUNCH
+    c->launches++;
+    return LBM_OK;
+}
+
+// Tile variants: rows per block, resident blocks per SM, register pipelining (lbm3d_pair.cuh).
+struct PairVariant { int ty, minb, pipe; };
+static const PairVariant PAIR_VARIANTS[] = {{20, 1, 0}, {16, 1, 1}, {10, 2, 0}, {16, 1, 0}, {18, 1, 0}, {8, 2, 1}};
+static const int PAIR_NVARIANTS = (int)(sizeof(PAIR_VARIANTS) / sizeof(PAIR_VARIANTS[0]));
+static const int PAIR_DEFAULT_VARIANT = 0;
+
+static int pair_variant(const lbm_ctx *c) {
+    return (c->pair_variant >= 0 && c->pair_variant < PAIR_NVARIANTS) ? c->pair_variant : PAIR_DEFAULT_VARIANT;
+}
+static int pair_ty(const lbm_ctx *c) { return PAIR_VARIANTS[pair_variant(c)].ty; }
+
+static int launch_pair(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, cudaStream_t st) {
+    switch (pair_variant(c)) {
+        case 0: return launch_pair_v<20, 1, false>(c, p, grid, st);
+        case 1: return launch_pair_v<16, 1, true>(c, p, grid, st);
+        case 2: return launch_pair_v<10, 2, false>(c, p, grid, st);
+        case 3: return launch_pair_v<16, 1, false>(c, p, grid, st);
+        case 4: return launch_pair_v<18, 1, false>(c, p, grid, st);
+        default: return launch_pair_v<8, 2, true>(c, p, grid, st);
+    }
+}
+
+static bool pair_enabled(const lbm_ctx *c) {
+    if (c->prm.dim != 3 || c->prm.nranks != 1) return false;
+    if (c->pair >= 0) return c->pair != 0;
+    return false;
+}
+
+// Iterations t = steps and t+1 in ONE pass: reads lat[cur] = S(t-1), writes lat[cur^1] = S(t+1).
+static int run_pair(lbm_ctx *c) {
+    lbm3d::KP p = make_kp(c);
+    const long long t = c->steps;
+    kp_set_lattices(c, &p, c->lat[c->cur], c->lat[c->cur ^ 1]);
+    p.side_rd = side_slot(c, t + 2);  p.side_wr = side_slot(c, t);
+    p.side_rd2 = side_slot(c, t + 3); p.side_wr2 = side_slot(c, t + 1);
+    p.zlo = 0; p.zhi = c->nzl;
+    p.Lz = c->pair_lz > 0 ? c->pair_lz : 64;
+    if (p.Lz > c->nzl) p.Lz = c->nzl;
+    const int ty = pair_ty(c);
+    const dim3 grid((c->N + lbm3d::PAIR_OX - 1) / lbm3d::PAIR_OX, (c->N + ty - 3) / (ty - 2), (c->nzl + p.Lz - 1) / p.Lz);
+    int rc = launch_pair(c, p, grid, c->s_main);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    c->cur ^= 1;
+    c->steps += 2;
+    c->f_valid = false;
+    c->residual_ready = false;
+    return LBM_OK;
+}
+
 static long long blocks_per_plane(const lbm_ctx *c) {
     dim3 blk, g;
     choose_block(c, &blk, &g);
@@ -157,7 +241,7 @@ static int halo_exchange(lbm_ctx *c, double *L, cudaStream_t st) {
 static const int GRAPH_LEN = 60;
 
 static void drop_graphs(lbm_ctx *c) {
-    for (int k = 0; k < 6; k++)
+    for (int k = 0; k < 8; k++)
         if (c->graph_exec[k]) { cudaGraphExecDestroy(c->graph_exec[k]); c->graph_exec[k] = nullptr; }
 }
 
@@ -171,7 +255,7 @@ static int run_iteration(lbm_ctx *c, int mode);
 
 // GRAPH_LEN plain iterations as one graph launch (captured on first use of each phase).
 static int run_graph_block(lbm_ctx *c) {
-    const int phase = (int)(c->steps % 3) * 2 + c->cur;
+    const int phase = (int)(c->steps % SIDE_DEPTH) * 2 + c->cur;
     if (!c->graph_exec[phase]) {
         const long long steps0 = c->steps, launches0 = c->launches;
         const int cur0 = c->cur;
@@ -188,7 +272,7 @@ static int run_graph_block(lbm_ctx *c) {
         if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
     }
     CK(cudaGraphLaunch(c->graph_exec[phase], c->s_main));
-    c->steps += GRAPH_LEN;        // GRAPH_LEN is even and a multiple of 3: cur and the side slot phase are unchanged
+    c->steps += GRAPH_LEN;        // GRAPH_LEN is a multiple of 4: cur and the side slot phase are unchanged
     c->launches += GRAPH_LEN;
     c->f_valid = false;
     c->residual_ready = false;
@@ -205,9 +289,8 @@ static int run_iteration(lbm_ctx *c, int mode) {
     const long long t = real ? c->steps : c->steps - 1;
     const int src_i = real ? c->cur : (c->cur ^ 1);
     kp_set_lattices(c, &p, c->lat[src_i], c->lat[src_i ^ 1]);
-    const long long side_n = (long long)c->nzl * c->N;
-    p.side_rd = c->side + ((t + 1) % 3) * side_n;  // written by iteration t-2
-    p.side_wr = c->side + (t % 3) * side_n;
+    p.side_rd = side_slot(c, t + 2);  // written by iteration t-2
+    p.side_wr = side_slot(c, t);
     const long long bpp = (long long)gxy.x * gxy.y;
 
     const bool multi = c->prm.nranks > 1;
@@ -241,7 +324,7 @@ static int run_iteration(lbm_ctx *c, int mode) {
             const long long rel = t - c->p2p_base;
             const int r = c->prm.rank, P = c->prm.nranks;
             lbm3d::k_wait_arrivals<<<1, 1, 0, c->s_halo>>>(c->sig, r > 0 ? rel : 0, r + 1 < P ? rel : 0, c->d_flag,
-                                                            20000000000LL);
+                                                            (unsigned long long)c->halo_timeout_ms * 1000000ULL);
             c->launches++;
             const int dsti = src_i ^ 1;
             for (int a = 0; a < 5; a++) {

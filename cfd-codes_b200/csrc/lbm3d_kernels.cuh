@@ -51,7 +51,7 @@ struct KP {
     // 38 accesses of a cell (one IMAD.WIDE each instead of 64-bit multiply chains):
     //   srcq[q][cell] = S_old[x - c_q][q]   (base already shifted by -(cx + cy*N + cz*N^2))
     //   dstq[q][cell] = S_new[x][q]
-    // with cell = (kl+1)*N^2 + j*N + i (ghost plane first).  The lattices are allocated with
+    // with cell = (kl+G)*N^2 + j*N + i (G ghost planes first).  The lattices are allocated with
     // N^2+N+1 elements of padding at both ends, so the shifted reads of box-boundary cells stay
     // inside the allocation (their values are discarded, see k_step).
     const double *srcq[19];
@@ -59,12 +59,16 @@ struct KP {
     double *Fbuf;        // F buffer [q][nzl*N2] (no ghosts), may be null for MODE_STEP
     const double *side_rd;  // stale f14 of the x=N-1 face, [nzl][N] (written two iterations ago)
     double *side_wr;        // slot this iteration writes
+    const double *side_rd2; // the same for the second iteration of k_step_pair
+    double *side_wr2;
     double *partials;    // per-block partial sums (MODE_STEP_DIFF_STOREF)
     int *flag;           // sticky negative-feq flag
     int N, M;            // grid points per side, N-1
     int Mz;              // global N-1 along z
     int nzl, k0;         // owned planes, global index of local plane 0
     int kl0, kstride;    // this launch covers local planes kl0 + blockIdx.z * kstride
+    int G;               // ghost planes below local plane 0 (cell = (kl+G)*N^2 + j*N + i)
+    int zlo, zhi, Lz;    // k_step_pair: output planes [zlo, zhi) of this launch, planes per z segment
     int partial_base;    // offset of this launch's block partials
     long long N2, PS, FS;
     double omega, omegam, omomega, gammainv;   // 3D:21,23,30,40
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(LBM_STEP_MAX_THREADS, LBM_STEP_MIN_BLOCKS) k_s
         const int cls = LBM_CLS(bx, by, bz);
         const int N1 = p.N;
         const int rowcell = j * N1 + i;
-        const int cell = (kl + 1) * (int)p.N2 + rowcell;   // < 2^31 (checked by the host)
+        const int cell = (kl + p.G) * (int)p.N2 + rowcell;   // < 2^31 (checked by the host)
 
         double f[Q];
         // 1. pull: unconditional, coalesced 8-byte loads through the pre-shifted bases.
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(128, LBM_STEP2_MIN_BLOCKS) k_step_x2(const __g
     const int bxb = (i0 + 1 == p.M) ? 2 : 0;           // cell b = (i0+1, j, k): can only touch x = N-1
     const int clsa = LBM_CLS(bxa, by, bz), clsb = LBM_CLS(bxb, by, bz);
     const int N1 = p.N;
-    const int cell = (kl + 1) * (int)p.N2 + j * N1 + i0;
+    const int cell = (kl + p.G) * (int)p.N2 + j * N1 + i0;
 
     double fa[Q], fb[Q];
 #define LBM_PULL2(q, cx, cy, cz, wq)                                                                 \
@@ -466,7 +470,7 @@ template <int METHOD>
 __global__ void __launch_bounds__(128, 4) k_collide_cells(const __grid_constant__ KP p, const int with_ghosts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    const int kl = (int)blockIdx.z - (with_ghosts ? 1 : 0);
+    const int kl = (int)blockIdx.z - (with_ghosts ? p.G : 0);
     if (i >= p.N || j >= p.N) return;
     const long long rowcell = (long long)j * p.N + i;
     double f[Q];
@@ -481,7 +485,7 @@ __global__ void __launch_bounds__(128, 4) k_collide_cells(const __grid_constant_
     }
     const bool neg = collide<METHOD, false>(f, p);
     if (neg) atomicOr(p.flag, 1);
-    const int cell = (kl + 1) * (int)p.N2 + (int)rowcell;
+    const int cell = (kl + p.G) * (int)p.N2 + (int)rowcell;
 #pragma unroll
     for (int q = 0; q < Q; q++) p.dstq[q][cell] = f[q];
 }
@@ -493,6 +497,13 @@ __global__ void k_fill_w(double *F, long long FS) {
 #define LBM_FILLW(q, cx, cy, cz, wq) F[(long long)(q) * FS + n] = (wq);
     LBM_D3Q19_VEL(LBM_FILLW)
 #undef LBM_FILLW
+}
+
+// out[r] = plane[r*N + N-1]: the x = N-1 column of one population over all (k, j) rows (lbm_set_f:
+// rebuilds the stale-f14 history from an uploaded state).
+__global__ void k_gather_xmax(const double *__restrict__ plane, int N, long long rows, double *__restrict__ out) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) out[r] = plane[r * N + (N - 1)];
 }
 
 __global__ void k_fill(double *a, long long n, double v) {
@@ -528,13 +539,20 @@ __global__ void __launch_bounds__(256) k_macrovars(const double *__restrict__ F,
 
 // Wait (one thread) until both neighbours have published `need` in this GPU's arrival flags, i.e.
 // their slab-boundary kernels of the previous iteration -- the ones that fill my ghost planes and
-// read the ghost planes I am about to overwrite -- are complete.  Bounded: after `timeout` cycles the
-// error bit 4 is raised instead of hanging the GPU.
+// read the ghost planes I am about to overwrite -- are complete.  Bounded in WALL-CLOCK time
+// (%globaltimer, nanoseconds; independent of the SM clock): after `timeout_ns` the error bit 4 is
+// raised instead of hanging the GPU.  Ranks must therefore stay within that skew of each other
+// (include/lbm_b200.h, option halo_timeout_ms).
+__device__ __forceinline__ unsigned long long lbm_globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __global__ void k_wait_arrivals(const volatile long long *sig, long long need_dn, long long need_up, int *flag,
-                                long long timeout) {
-    const long long t0 = clock64();
+                                unsigned long long timeout_ns) {
+    const unsigned long long t0 = lbm_globaltimer_ns();
     while (sig[0] < need_dn || sig[1] < need_up) {
-        if (clock64() - t0 > timeout) { atomicOr(flag, 4); break; }
+        if (lbm_globaltimer_ns() - t0 > timeout_ns) { atomicOr(flag, 4); break; }
         __nanosleep(200);
     }
     __threadfence_system();

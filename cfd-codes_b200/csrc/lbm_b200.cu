@@ -18,6 +18,7 @@
 
 #include "../../include/lbm_b200.h"
 #include "lbm3d_kernels.cuh"
+#include "lbm3d_pair.cuh"
 #include "lbm2d_kernels.cuh"
 #include "lbm_ctx.h"
 #include "lbm3d_host.inl"
@@ -50,14 +51,28 @@ int lbm_nccl_unique_id(unsigned char out[LBM_NCCL_ID_BYTES]) {
 int lbm_destroy(lbm_ctx *c) {
     if (!c) return LBM_OK;
     cudaSetDevice(c->dev);
+    bool peers_quiet = true;
     if (c->p2p && c->s_halo && c->steps > c->p2p_base) {
         // the neighbours' last boundary kernels store into my ghost planes: let them land first
         const long long rel = c->steps - c->p2p_base;
         lbm3d::k_wait_arrivals<<<1, 1, 0, c->s_halo>>>(c->sig, c->prm.rank > 0 ? rel : 0,
-                                                        c->prm.rank + 1 < c->prm.nranks ? rel : 0, c->d_flag, 4000000000LL);
+                                                        c->prm.rank + 1 < c->prm.nranks ? rel : 0, c->d_flag,
+                                                        (unsigned long long)c->halo_timeout_ms * 1000000ULL);
+        int flag = 0;
+        if (cudaStreamSynchronize(c->s_halo) == cudaSuccess &&
+            cudaMemcpy(&flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess && (flag & 4))
+            peers_quiet = false;
     }
     if (c->s_main) cudaStreamSynchronize(c->s_main);
     if (c->s_halo) cudaStreamSynchronize(c->s_halo);
+    if (!peers_quiet) {
+        // A neighbour never reported its last boundary kernel: it may still be storing into this
+        // context's ghost planes.  Freeing them now could hand that memory to somebody else, so the
+        // device buffers are deliberately leaked and the caller is told.
+        if (c->comm) g_nccl.CommDestroy(c->comm);
+        delete c;
+        return fail(LBM_ERR_CUDA, "lbm_destroy: a neighbour GPU did not finish within halo_timeout_ms; device memory of this context was not freed");
+    }
     for (int side = 0; side < 2; side++)
         for (int a = 0; a < 3; a++)
             if (c->peer_ipc[side][a]) cudaIpcCloseMemHandle(c->peer_ipc[side][a]);
@@ -91,7 +106,8 @@ static int create3d(lbm_ctx *c) {
     c->k1 = (int)((long long)(p.rank + 1) * p.N / p.nranks);
     c->nzl = c->k1 - c->k0;
     if (c->nzl < 1) return fail(LBM_ERR_INVALID, "rank %d of %d owns no plane of N=%d", p.rank, p.nranks, p.N);
-    c->PS = (long long)(c->nzl + 2) * c->N2;
+    c->G = 1;
+    c->PS = (long long)(c->nzl + 2 * c->G) * c->N2;
     c->FS = (long long)c->nzl * c->N2;
     if (c->PS >= (1LL << 31)) return fail(LBM_ERR_INVALID, "more than 2^31 cells per GPU");
 
@@ -122,7 +138,7 @@ static int create3d(lbm_ctx *c) {
         c->lat[l] = c->lat_alloc[l] + c->pad;
     }
     const long long side_n = (long long)c->nzl * c->N;
-    if ((rc = dev_alloc(c, &c->side, 3 * side_n))) return rc;
+    if ((rc = dev_alloc(c, &c->side, SIDE_DEPTH * side_n))) return rc;
     if ((rc = dev_alloc(c, &c->d_red, 2))) return rc;
     if ((rc = dev_alloc(c, &c->d_flag, 1))) return rc;
     CK(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->s_main));
@@ -130,7 +146,7 @@ static int create3d(lbm_ctx *c) {
     CK(cudaMallocHost((void **)&c->h_pin, 4 * sizeof(double)));
 
     // stale-f14 history starts at the initial value w[14] = 1/36 (3D:192-205)
-    lbm3d::k_fill<<<(unsigned)((3 * side_n + 255) / 256), 256, 0, c->s_main>>>(c->side, 3 * side_n, LBM_W2);
+    lbm3d::k_fill<<<(unsigned)((SIDE_DEPTH * side_n + 255) / 256), 256, 0, c->s_main>>>(c->side, SIDE_DEPTH * side_n, LBM_W2);
     c->launches++;
 
     // S(-1) = collide(f = w) in both lattices incl. ghost planes (colliding the initial equilibrium
@@ -141,7 +157,7 @@ static int create3d(lbm_ctx *c) {
         lbm3d::KP kp = make_kp(c);
         kp_set_lattices(c, &kp, nullptr, c->lat[l]);
         kp.Fbuf = nullptr;
-        dim3 grid(gxy.x, gxy.y, c->nzl + 2);
+        dim3 grid(gxy.x, gxy.y, c->nzl + 2 * c->G);
         if (p.METHOD == 1) lbm3d::k_collide_cells<1><<<grid, blk, 0, c->s_main>>>(kp, 1);
         else               lbm3d::k_collide_cells<0><<<grid, blk, 0, c->s_main>>>(kp, 1);
         c->launches++;
@@ -316,16 +332,21 @@ int lbm_step(lbm_ctx *c, long long n) {
         if ((rc = ensure_partials(c))) return rc;
         if (n == 1 && !c->f_valid) { if ((rc = materialise_F(c))) return rc; }
     }
-    const long long n_plain = track ? n - 2 : n;  // the leading iterations run the plain step kernel
+    // The leading iterations run the plain step kernel: all but the last two when the residual is
+    // tracked (STOREF, DIFF_STOREF), all but the last one otherwise -- the final iteration is always
+    // a single step, so that lat[cur^1] holds S(t-1) and the reference's f2 can be re-materialised.
+    const bool use_pairs = pair_enabled(c);
+    const long long n_plain = track ? n - 2 : (use_pairs ? n - 1 : n);
     lbm_ctx::Span sp{nullptr, nullptr, 0};
     if (n_plain > 0) {
         if (c->spans.size() > 256) resolve_spans(c, false);
         sp.a = span_event(c);
         sp.b = span_event(c);
+        if (!sp.a || !sp.b) return fail(LBM_ERR_CUDA, "cudaEventCreate failed");
         sp.iters = n_plain;
         CK(cudaEventRecord(sp.a, c->s_main));
     }
-    const bool use_graphs = graphs_enabled(c);
+    const bool use_graphs = graphs_enabled(c) && !use_pairs;
     for (long long t = 0; t < n; t++) {
         int mode = lbm3d::MODE_STEP;
         if (track) {
@@ -335,6 +356,9 @@ int lbm_step(lbm_ctx *c, long long n) {
         if (use_graphs && t + GRAPH_LEN <= n_plain) {
             if ((rc = run_graph_block(c))) return rc;
             t += GRAPH_LEN - 1;
+        } else if (use_pairs && t + 2 <= n_plain) {
+            if ((rc = run_pair(c))) return rc;                       // two iterations, one pass over HBM
+            t += 1;
         } else if ((rc = run_iteration(c, mode))) {
             return rc;
         }
@@ -429,30 +453,24 @@ int lbm_set_f(lbm_ctx *c, const double *host_f, const double *host_f_prev) {
     for (int q = 0; q < lbm3d::Q; q++)
         CK(cudaMemcpyAsync(c->Fbuf + (long long)q * c->FS, host_f + (long long)q * N3 + hk0 * c->N2,
                            (size_t)c->FS * sizeof(double), cudaMemcpyHostToDevice, c->s_main));
-    // stale f14 of the x = N-1 face: the next iteration (index `steps`) reads slot (steps+1)%3.
-    // Taken from the reference's other buffer if given, else from the current one.
+    // Stale f14 of the x = N-1 face (3D:421): iteration t = steps reads the slot iteration t-2 wrote --
+    // that value lives in the reference's OTHER buffer (host_f_prev) -- and iteration t+1 reads what
+    // t-1 wrote: this state's own post-BC f14.  The latter is gathered on the device from the uploaded
+    // F buffer; the former is one strided copy of the column (no host staging, no extra sync).
     {
-        const double *srcf = host_f_prev ? host_f_prev : host_f;
         const long long side_n = (long long)c->nzl * c->N;
-        double *tmp = (double *)malloc((size_t)side_n * sizeof(double));
-        if (!tmp) return fail(LBM_ERR_NOMEM, "malloc");
-        for (int kl = 0; kl < c->nzl; kl++)
-            for (int j = 0; j < c->N; j++)
-                tmp[(long long)kl * c->N + j] = srcf[14LL * N3 + (hk0 + kl) * c->N2 + (long long)j * c->N + (c->N - 1)];
-        // slot read by iteration t = steps is (t+1)%3; the one read by t+1 is (t+2)%3 and must be
-        // this state's own post-BC f14, which is in host_f.
-        cudaError_t e = cudaMemcpyAsync(c->side + ((c->steps + 1) % 3) * side_n, tmp, (size_t)side_n * sizeof(double),
-                                        cudaMemcpyHostToDevice, c->s_main);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_main);
-        for (int kl = 0; kl < c->nzl; kl++)
-            for (int j = 0; j < c->N; j++)
-                tmp[(long long)kl * c->N + j] = host_f[14LL * N3 + (hk0 + kl) * c->N2 + (long long)j * c->N + (c->N - 1)];
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(c->side + ((c->steps + 2) % 3) * side_n, tmp, (size_t)side_n * sizeof(double),
-                                cudaMemcpyHostToDevice, c->s_main);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_main);
-        free(tmp);
-        if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "side upload: %s", cudaGetErrorString(e));
+        const unsigned gb = (unsigned)((side_n + 255) / 256);
+        lbm3d::k_gather_xmax<<<gb, 256, 0, c->s_main>>>(c->Fbuf + 14LL * c->FS, c->N, side_n, side_slot(c, c->steps + 3));
+        c->launches++;
+        if (host_f_prev) {
+            CK(cudaMemcpy2DAsync(side_slot(c, c->steps + 2), sizeof(double),
+                                 host_f_prev + 14LL * N3 + hk0 * c->N2 + (c->N - 1), (size_t)c->N * sizeof(double),
+                                 sizeof(double), (size_t)side_n, cudaMemcpyHostToDevice, c->s_main));
+        } else {
+            lbm3d::k_gather_xmax<<<gb, 256, 0, c->s_main>>>(c->Fbuf + 14LL * c->FS, c->N, side_n, side_slot(c, c->steps + 2));
+            c->launches++;
+        }
+        CK(cudaGetLastError());
     }
     // S = collide(F) into lat[cur]
     dim3 blk, gxy;
@@ -518,13 +536,42 @@ int lbm_set_option(lbm_ctx *c, const char *key, long long value) {
         c->graphs = value < 0 ? -1 : (value != 0);
         return LBM_OK;
     }
-    if (!strcmp(key, "block_x")) {
-        const int lim = c->prm.dim == 2 ? 256 : 128;
-        if (value < 0 || value > lim || (value % 32)) return fail(LBM_ERR_INVALID, "block_x must be a multiple of 32 <= %d", lim);
-        c->block_x = (int)value;
-    } else if (!strcmp(key, "block_y")) {
-        if (value < 0 || value > 256) return fail(LBM_ERR_INVALID, "block_y out of range");
-        c->block_y = (int)value;
+    if (!strcmp(key, "block_x") || !strcmp(key, "block_y")) {
+        // Validate the EFFECTIVE block shape (explicit values mixed with automatic ones) before
+        // committing it; a rejected value leaves the context unchanged.
+        const bool is_x = key[6] == 'x';
+        const int lim = c->prm.dim == 2 ? 256 : LBM_STEP_MAX_THREADS;
+        if (is_x && (value < 0 || value > lim || (value % 32)))
+            return fail(LBM_ERR_INVALID, "block_x must be a multiple of 32 <= %d (0 = automatic)", lim);
+        if (!is_x && (value < 0 || value > lim)) return fail(LBM_ERR_INVALID, "block_y must be in [0, %d] (0 = automatic)", lim);
+        const int old_x = c->block_x, old_y = c->block_y;
+        if (is_x) c->block_x = (int)value; else c->block_y = (int)value;
+        if (c->prm.dim == 3) {
+            dim3 blk, g;
+            choose_block(c, &blk, &g);
+            if (blk.x * blk.y > (unsigned)LBM_STEP_MAX_THREADS) {
+                c->block_x = old_x; c->block_y = old_y;
+                return fail(LBM_ERR_INVALID, "block %ux%u has more than %d threads", blk.x, blk.y, LBM_STEP_MAX_THREADS);
+            }
+        } else if (c->block_x > 0 && c->block_y > 0 && c->block_x * c->block_y > 256) {
+            c->block_x = old_x; c->block_y = old_y;
+            return fail(LBM_ERR_INVALID, "block_x*block_y > 256");
+        }
+    } else if (!strcmp(key, "pair")) {
+        c->pair = value < 0 ? -1 : (value != 0);
+        return LBM_OK;
+    } else if (!strcmp(key, "pair_variant")) {
+        if (value < -1 || value >= PAIR_NVARIANTS) return fail(LBM_ERR_INVALID, "pair_variant must be in [-1, %d)", PAIR_NVARIANTS);
+        c->pair_variant = (int)value;
+        return LBM_OK;
+    } else if (!strcmp(key, "pair_lz")) {
+        if (value < 0) return fail(LBM_ERR_INVALID, "pair_lz must be >= 0");
+        c->pair_lz = (int)value;
+        return LBM_OK;
+    } else if (!strcmp(key, "halo_timeout_ms")) {
+        if (value < 1) return fail(LBM_ERR_INVALID, "halo_timeout_ms must be >= 1");
+        c->halo_timeout_ms = value;
+        return LBM_OK;
     } else if (!strcmp(key, "vec2")) {
         c->vec2 = value != 0;
         return LBM_OK;
@@ -538,8 +585,6 @@ int lbm_set_option(lbm_ctx *c, const char *key, long long value) {
     } else {
         return fail(LBM_ERR_INVALID, "unknown option %s", key);
     }
-    if (c->prm.dim == 3 && c->block_x > 0 && c->block_y > 0 && c->block_x * c->block_y > 128)
-        return fail(LBM_ERR_INVALID, "block_x*block_y > 128");
     // partial-sum buffer depends on the block shape
     if (c->prm.dim == 3 && c->prm.track_residual) return ensure_partials(c);
     return LBM_OK;

@@ -82,6 +82,7 @@ struct lbm_ctx {
     bool halo_pending = false;  // ev_halo has been recorded and not yet waited on by s_main
 
     int N = 0, nzl = 0, k0 = 0, k1 = 0;
+    int G = 1;                            // ghost planes on each side of the slab in lat[]
     long long N2 = 0, PS = 0, FS = 0;
     double NU, TAU, OMEGA, OMEGAm, OmOMEGA, gammainv, ulid, vlid, wlid;
 
@@ -91,7 +92,7 @@ struct lbm_ctx {
     int cur = 0;                          // lat[cur] holds S of the latest iteration
     double *Fbuf = nullptr;               // the reference's f2 of the latest iteration when f_valid
     bool f_valid = false;
-    double *side = nullptr;               // [3][nzl][N] stale-f14 history of the x = N-1 face
+    double *side = nullptr;               // [SIDE_DEPTH][nzl][N] stale-f14 history of the x = N-1 face
     double *partials = nullptr;
     long long npartials = 0;
     double *d_red = nullptr;  // [0] local sum, [1] all-reduced sum
@@ -118,11 +119,13 @@ struct lbm_ctx {
     int block_x = 0, block_y = 0;
     int vec2 = 0;  // 1: plain iterations use the two-cells-per-thread 128-bit kernel (N even)
     // CUDA graphs for launch-bound grids (single GPU): GRAPH_LEN consecutive plain iterations per
-    // graph launch.  The kernel arguments of iteration t depend on (lattice parity, t mod 3), a
-    // 6-periodic pattern; GRAPH_LEN is a multiple of 6, so a graph captured in one phase leaves the
-    // context in the same phase and can be replayed back to back.
+    // graph launch.  The kernel arguments of iteration t depend on (lattice parity, t mod 4);
+    // GRAPH_LEN is a multiple of 4, so a graph captured in one phase leaves the context in the same
+    // phase and can be replayed back to back.
     int graphs = -1;                         // -1 auto (small grids), 0 off, 1 on
-    cudaGraphExec_t graph_exec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaGraphExec_t graph_exec[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // two iterations per pass (k_step_pair): -1 auto, 0 off, 1 on; tile variant (PAIR_VARIANTS, -1 = default); planes per z segment
+    int pair = -1, pair_variant = -1, pair_lz = 0;
     // direct NVLink halo (lbm_peer_connect): neighbours' lattices / arrival flags mapped here
     bool p2p = false;
     long long p2p_base = 0;               // iteration count at which the direct halo was switched on
@@ -133,6 +136,7 @@ struct lbm_ctx {
     void *peer_ipc[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // opened IPC mappings to close
     int peer_nzl[2] = {0, 0};
     long long peer_PS[2] = {0, 0};
+    long long halo_timeout_ms = 600000;   // direct halo: wall-clock limit of one wait for a neighbour (option halo_timeout_ms)
     bool host_local = false;  // host arrays are compact local slabs instead of full LU4/LU3 arrays
     ncclComm_t comm = nullptr;
 };
@@ -150,9 +154,12 @@ static int dev_alloc(lbm_ctx *c, T **p, long long count) {
 
 static int poll_flag(lbm_ctx *c) {
     int flag = 0;
+    // the slab-boundary kernel of the last iteration runs on s_halo and may still raise a bit:
+    // drain it BEFORE the flag is read
+    if (c->s_halo) CK(cudaStreamSynchronize(c->s_halo));
+    c->halo_pending = false;
     CK(cudaMemcpyAsync(&flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->s_main));
     CK(cudaStreamSynchronize(c->s_main));
-    if (c->s_halo) CK(cudaStreamSynchronize(c->s_halo));
     if (flag & 4) return fail(LBM_ERR_CUDA, "direct halo: timed out waiting for a neighbour GPU's arrival flag");
     if (flag & 1) c->unstable = true;
     if (c->unstable) return fail(LBM_ERR_UNSTABLE, "Error: negative feq.  Therefore, unstable.");

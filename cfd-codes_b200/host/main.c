@@ -19,6 +19,16 @@
  *   - LUPS is computed in double (the reference's `N3 * skip` overflows int for N >= 163, 3D:117);
  *   - a negative equilibrium is detected at the next residual check (<= skip iterations late)
  *     instead of immediately; message and exit status are the reference's (3D:687-692).
+ * Kept on purpose: when the loop ends by reaching MAXITER without converging, the reference has
+ * already swapped its buffers, so datwrite's macrovars(f2) reads the state of iteration MAXITER-2
+ * (3D:104-127); this program writes that same state (the fields are taken one iteration before the
+ * last).  With MAXITER <= 1 the reference would print the initial state; here the state after
+ * iteration 0 is written.
+ *
+ * Errors: a failing library call makes the worker print the reference's message and return its
+ * status to main(), which exits 1.  With --gpus > 1 the other workers share an NCCL communicator
+ * with the failed rank and could wait for it forever, so the process is ended with _exit(1) (no
+ * atexit handlers or destructors run while sibling threads are still inside CUDA/NCCL).
  */
 #include <math.h>
 #include <pthread.h>
@@ -26,6 +36,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -55,15 +66,29 @@ static double now(void) {
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
-static void die_lbm(int rc) {
+static int g_gpus = 1;
+
+/* Report a failed library call the way the reference reports its own errors (3D:687-692, 335-344).
+ * Single GPU: returns so that the worker can hand the status to main().  Several GPUs: see "Errors"
+ * in the header comment. */
+static void report_lbm(int rc) {
     if (rc == LBM_ERR_UNSTABLE) {
         printf("Error: negative feq.  Therefore, unstable.\n"); /* 3D:689 */
     } else {
         printf("Error: %s\n", lbm_last_error());
     }
     fflush(stdout);
-    exit(1);
+    if (g_gpus > 1) _exit(1);
 }
+#define LBM_TRY(call)                                   \
+    do {                                                \
+        if ((rc = (call))) {                            \
+            report_lbm(rc);                             \
+            if (ctx) lbm_destroy(ctx);                  \
+            w->status = 1;                              \
+            return NULL;                                \
+        }                                               \
+    } while (0)
 
 /* Writes the Tecplot file, 3D:363-382: i outer, j, k inner; x = y = z = linspace(0, N-1, N) (3D:175).
  * Same bytes as the reference's fprintf("%.10f, ...") loop, produced by an exact integer formatter
@@ -131,15 +156,15 @@ static void *run(void *arg) {
     if (o->gpus > 1) memcpy(p.nccl_id, w->nccl_id, LBM_NCCL_ID_BYTES);
 
     lbm_ctx *ctx = NULL;
-    int rc = lbm_create(&p, &ctx); /* allocate(); initialize();  3D:76-78 */
-    if (rc) die_lbm(rc);
+    int rc;
+    LBM_TRY(lbm_create(&p, &ctx)); /* allocate(); initialize();  3D:76-78 */
     lbm_info info;
     lbm_get_info(ctx, &info);
     if (o->halo == 1 && o->gpus > 1) { /* fused direct-NVLink halo instead of NCCL send/recv */
-        if ((rc = lbm_peer_export(ctx, w->blobs[w->rank]))) die_lbm(rc);
+        LBM_TRY(lbm_peer_export(ctx, w->blobs[w->rank]));
         pthread_barrier_wait(w->bar);
-        if ((rc = lbm_peer_connect(ctx, w->rank > 0 ? w->blobs[w->rank - 1] : NULL,
-                                   w->rank + 1 < o->gpus ? w->blobs[w->rank + 1] : NULL))) die_lbm(rc);
+        LBM_TRY(lbm_peer_connect(ctx, w->rank > 0 ? w->blobs[w->rank - 1] : NULL,
+                                 w->rank + 1 < o->gpus ? w->blobs[w->rank + 1] : NULL));
         pthread_barrier_wait(w->bar);
     }
 
@@ -155,29 +180,43 @@ static void *run(void *arg) {
     }
 
     /* First iteration, 3D:94-100 */
-    double df, df0;
-    if ((rc = lbm_step(ctx, 1))) die_lbm(rc);
-    if ((rc = lbm_residual(ctx, &df0))) die_lbm(rc);
+    double df = 0.0, df0;
+    LBM_TRY(lbm_step(ctx, 1));
+    LBM_TRY(lbm_residual(ctx, &df0));
     if (root) {
         printf("\nIteration 0:\n");
         printf("df:\t%.3e\n", df0);
     }
     df0 = 1.0 / df0;
 
-    /* Rest of iterations, 3D:103-124: iteration t is checked when t % skip == 0 */
+    /* Rest of iterations, 3D:103-124: iteration t is checked when t % skip == 0.  `fields_taken`:
+     * the output fields were already read one iteration before the last (MAXITER exit, see header). */
     double start = now();
     const double cells = (double)o->N * (double)o->N * (double)o->N;
     long long t = 1;
     const long long last = (long long)o->MAXITER - 1;
+    int fields_taken = 0;
     while (t <= last) {
         long long T = ((t + o->skip - 1) / o->skip) * o->skip; /* next check iteration */
-        if (T > last) {
-            if ((rc = lbm_step(ctx, last - t + 1))) die_lbm(rc);
-            if ((rc = lbm_sync(ctx))) die_lbm(rc);
-            break;
+        const int final_block = (T >= last);
+        const long long stop_at = final_block ? last : T; /* last iteration of this block */
+        if (final_block) {
+            /* run up to iteration last-1, take the fields the reference would print if this block
+             * does not converge, then do the final iteration */
+            if (stop_at - t > 0) LBM_TRY(lbm_step(ctx, stop_at - t));
+            if (o->SAVETXT == 1) {
+                LBM_TRY(lbm_macrovars(ctx, w->u1, w->u2, w->u3, NULL, w->vmag));
+                fields_taken = 1;
+            }
+            LBM_TRY(lbm_step(ctx, 1));
+            if (T > last) { /* no residual check at the final iteration */
+                LBM_TRY(lbm_sync(ctx));
+                break;
+            }
+        } else {
+            LBM_TRY(lbm_step(ctx, T - t + 1));
         }
-        if ((rc = lbm_step(ctx, T - t + 1))) die_lbm(rc);
-        if ((rc = lbm_residual(ctx, &df))) die_lbm(rc);
+        LBM_TRY(lbm_residual(ctx, &df));
         df *= df0;
         const double stop = now() - start;
         if (root) {
@@ -188,13 +227,13 @@ static void *run(void *arg) {
             fflush(stdout);
         }
         start = now();
-        if (df < o->THRESH) break;
+        if (df < o->THRESH) { fields_taken = 0; break; } /* converged: the newest state is printed (3D:119-122) */
         t = T + 1;
     }
 
     /* Output to text file, 3D:127 */
     if (o->SAVETXT == 1) {
-        if ((rc = lbm_macrovars(ctx, w->u1, w->u2, w->u3, NULL, w->vmag))) die_lbm(rc);
+        if (!fields_taken) LBM_TRY(lbm_macrovars(ctx, w->u1, w->u2, w->u3, NULL, w->vmag));
         if (o->gpus > 1) pthread_barrier_wait(w->bar);
         if (root) datwrite(o, w->u1, w->u2, w->u3, w->vmag);
     }
@@ -242,10 +281,14 @@ int main(int argc, char **argv) {
         return 2;
     }
     printf("Threads used:\t%d\n", o.gpus); /* 3D:210 (here: GPUs) */
+    g_gpus = o.gpus;
 
     unsigned char id[LBM_NCCL_ID_BYTES];
     memset(id, 0, sizeof id);
-    if (o.gpus > 1 && lbm_nccl_unique_id(id)) die_lbm(LBM_ERR_NCCL);
+    if (o.gpus > 1 && lbm_nccl_unique_id(id)) {
+        printf("Error: %s\n", lbm_last_error());
+        return 1;
+    }
 
     double *u1 = NULL, *u2 = NULL, *u3 = NULL, *vmag = NULL;
     if (o.SAVETXT == 1) {
@@ -269,6 +312,8 @@ int main(int argc, char **argv) {
     }
     run(&ws[0]);
     for (int r = 1; r < o.gpus; r++) pthread_join(th[r], NULL);
+    int status = 0;
+    for (int r = 0; r < o.gpus; r++) status |= ws[r].status;
     free(u1); free(u2); free(u3); free(vmag); free(ws); free(th); free(blobs);
-    return 0;
+    return status ? 1 : 0;
 }

@@ -14,6 +14,9 @@
  * in-place sweep (same steady state) so iteration counts differ (94 000 vs 44 000 at
  * the defaults); any number of GPUs >= 1 (the reference insists on >= 3 MPI ranks, 2D:69-72);
  * MLUPS is computed in double (the reference's `prntInt * N * M` overflows int, 2D:472).
+ * Kept on purpose: the files hold u, v, rho of the LAST CHECK (2D:180-198), also when the loop ends
+ * at MAXITER some iterations after it.  A failing library call prints the message and makes main()
+ * return 1 (several GPUs: _exit(1), the sibling workers share an NCCL communicator with the failed one).
  */
 #include <math.h>
 #include <pthread.h>
@@ -21,6 +24,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "lbm_b200.h"
 
@@ -35,6 +39,7 @@ typedef struct {
     const unsigned char *nccl_id;
     pthread_barrier_t *bar;
     double *u, *v, *rho;
+    int status;
 } worker;
 
 static double now(void) {
@@ -43,11 +48,22 @@ static double now(void) {
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
-static void die_lbm(void) {
+static int g_gpus = 1;
+
+static void report_lbm(void) {
     printf("Error: %s\n", lbm_last_error());
     fflush(stdout);
-    exit(1);
+    if (g_gpus > 1) _exit(1);
 }
+#define LBM_TRY(call)                      \
+    do {                                   \
+        if ((call)) {                      \
+            report_lbm();                  \
+            if (ctx) lbm_destroy(ctx);     \
+            w->status = 1;                 \
+            return NULL;                   \
+        }                                  \
+    } while (0)
 
 /* outputScalar, 2D:482-495 (single writer: the slabs were gathered into one host array) */
 static void output_scalar(const options *o, const char *name, const double *a) {
@@ -69,7 +85,7 @@ static void *run(void *arg) {
     p.rank = w->rank; p.nranks = o->gpus; p.device = w->rank; p.track_residual = 0;
     if (o->gpus > 1) memcpy(p.nccl_id, w->nccl_id, LBM_NCCL_ID_BYTES);
     lbm_ctx *ctx = NULL;
-    if (lbm_create(&p, &ctx)) die_lbm();
+    LBM_TRY(lbm_create(&p, &ctx));
     lbm_info info;
     lbm_get_info(ctx, &info);
     if (root) { /* 2D:74-81 */
@@ -93,15 +109,21 @@ static void *run(void *arg) {
     const double cells = (double)o->N * (double)o->M;
     /* 2D:160-187: iteration t, then the check when t % prntInt == 0 */
     long long t = 0;
+    int fields_taken = 0;
     const long long maxiter = (long long)o->MAXITER;
     while (t < maxiter) {
         const long long T = (t == 0) ? 0 : ((t + o->prntInt - 1) / o->prntInt) * o->prntInt; /* next check iteration */
         if (T >= maxiter) {
-            if (lbm_step(ctx, maxiter - t)) die_lbm();
+            /* MAXITER ends the run between two checks: the files hold the fields of the last check */
+            if (o->SAVE && t > 0) {
+                LBM_TRY(lbm_macrovars(ctx, w->u, w->v, NULL, w->rho, NULL));
+                fields_taken = 1;
+            }
+            LBM_TRY(lbm_step(ctx, maxiter - t));
             break;
         }
-        if (lbm_step(ctx, T - t + 1)) die_lbm();
-        if (lbm_residual(ctx, &diff)) die_lbm(); /* macroVars + Allreduce + sqrt, 2D:419-460 */
+        LBM_TRY(lbm_step(ctx, T - t + 1));
+        LBM_TRY(lbm_residual(ctx, &diff)); /* macroVars + Allreduce + sqrt, 2D:419-460 */
         if (T == 0) {
             df0 = 1.0 / diff;
             if (root) printf("Iteration\tdf/df0\t\tMLUPS\n");
@@ -111,7 +133,7 @@ static void *run(void *arg) {
         if (root) {
             printf("%.3e\t%.3e\t%.1f\n", (double)T, df, (double)o->prntInt * cells / (1E6 * (stop - start)));
             fflush(stdout);
-            if (isinf(df)) exit(1); /* 2D:473 */
+            if (isinf(df)) { fflush(stdout); _exit(1); } /* 2D:473 */
         }
         start = stop;
         if (df < o->THRESH) break;
@@ -119,7 +141,7 @@ static void *run(void *arg) {
     }
     if (o->SAVE) {
         /* the reference writes u, v, rho of the LAST check (2D:190-202) = the state just examined */
-        if (lbm_macrovars(ctx, w->u, w->v, NULL, w->rho, NULL)) die_lbm();
+        if (!fields_taken) LBM_TRY(lbm_macrovars(ctx, w->u, w->v, NULL, w->rho, NULL));
         if (o->gpus > 1) pthread_barrier_wait(w->bar);
         if (root) {
             double *x = malloc((size_t)o->N * o->M * sizeof(double)), *y = malloc((size_t)o->N * o->M * sizeof(double));
@@ -134,6 +156,7 @@ static void *run(void *arg) {
         }
     }
     lbm_destroy(ctx);
+    w->status = 0;
     return NULL;
 }
 
@@ -164,7 +187,8 @@ int main(int argc, char **argv) {
     if (o.gpus < 1 || o.prntInt < 1) { fprintf(stderr, "bad --gpus / --prntInt\n"); return 2; }
     unsigned char id[LBM_NCCL_ID_BYTES];
     memset(id, 0, sizeof id);
-    if (o.gpus > 1 && lbm_nccl_unique_id(id)) die_lbm();
+    g_gpus = o.gpus;
+    if (o.gpus > 1 && lbm_nccl_unique_id(id)) { printf("Error: %s\n", lbm_last_error()); return 1; }
     const size_t n = (size_t)o.N * o.M;
     double *u = malloc(n * sizeof(double)), *v = malloc(n * sizeof(double)), *rho = malloc(n * sizeof(double));
     if (!u || !v || !rho) { printf("Error allocating memory!\n"); return 1; }
@@ -173,11 +197,13 @@ int main(int argc, char **argv) {
     worker *ws = calloc((size_t)o.gpus, sizeof(worker));
     pthread_t *th = calloc((size_t)o.gpus, sizeof(pthread_t));
     for (int r = 0; r < o.gpus; r++) {
-        ws[r] = (worker){.rank = r, .opt = &o, .nccl_id = id, .bar = &bar, .u = u, .v = v, .rho = rho};
+        ws[r] = (worker){.rank = r, .opt = &o, .nccl_id = id, .bar = &bar, .u = u, .v = v, .rho = rho, .status = 1};
         if (r > 0) pthread_create(&th[r], NULL, run, &ws[r]);
     }
     run(&ws[0]);
     for (int r = 1; r < o.gpus; r++) pthread_join(th[r], NULL);
+    int status = 0;
+    for (int r = 0; r < o.gpus; r++) status |= ws[r].status;
     free(u); free(v); free(rho); free(ws); free(th);
-    return 0;
+    return status ? 1 : 0;
 }

@@ -44,6 +44,26 @@ def test_lbm3d_cavity_reports_instability_like_the_reference(tmp_path):
     assert r.stdout.rstrip().endswith("Error: negative feq.  Therefore, unstable.")
 
 
+@pytest.mark.parametrize("maxiter,skip,steps_printed", [(41, 500, 40), (1001, 500, 1000), (31, 10, 30)])
+def test_lbm3d_cavity_maxiter_exit_prints_the_swapped_buffer(tmp_path, oracle, maxiter, skip, steps_printed):
+    """When the loop ends at MAXITER without converging, the reference has already swapped f1/f2, so
+    its datwrite prints the state of iteration MAXITER-2 (main.c:104-127) = `steps_printed` updates;
+    also at a MAXITER that falls right after a residual check."""
+    r = subprocess.run([EXE3, "--N", "12", "--MAXITER", str(maxiter), "--skip", str(skip), "--THRESH", "1e-30"],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    o = oracle.Oracle3D(N=12, Re=100, threads=2)
+    o.step(steps_printed)
+    mv = o.macrovars()
+    with open(tmp_path / "Solution_n=12Re=100_DIAG=0_2RT_M=0.250.dat") as fh:
+        fh.readline()
+        data = np.loadtxt(fh, delimiter=",")
+    # file order: i outer, j, k inner (main.c:373-376); oracle arrays are LU3 = [k][j][i]
+    for col, name in ((3, "u1"), (4, "u2"), (5, "u3"), (6, "vmag")):
+        want = mv[name].reshape(12, 12, 12).transpose(2, 1, 0).ravel()
+        assert np.array_equal(np.round(data[:, col] * 1e10), np.round(want * 1e10)), name
+
+
 def test_lbm2d_cavity_outputs(tmp_path):
     r = subprocess.run([EXE2, "--N", "40", "--M", "60", "--Re", "50", "--THRESH", "1e-6"], cwd=tmp_path,
                        capture_output=True, text=True, timeout=300)

@@ -35,7 +35,7 @@ PEER_BLOB_BYTES = 320
 ABI_SYMBOLS = [
     "lbm_default_params", "lbm_nccl_unique_id", "lbm_create", "lbm_peer_export", "lbm_peer_connect", "lbm_step", "lbm_step_timed", "lbm_timer_start",
     "lbm_timer_stop", "lbm_residual",
-    "lbm_get_f", "lbm_set_f", "lbm_macrovars", "lbm_sync", "lbm_get_info", "lbm_set_option", "lbm_destroy",
+    "lbm_get_f", "lbm_set_f", "lbm_set_f_async", "lbm_set_f_commit", "lbm_macrovars", "lbm_macrovars_async", "lbm_io_wait", "lbm_sync", "lbm_get_info", "lbm_set_option", "lbm_destroy",
     "lbm_last_error", "lbm_version",
 ]
 
@@ -56,6 +56,7 @@ class LbmInfo(C.Structure):
         ("Q", C.c_int), ("k0", C.c_int), ("k1", C.c_int), ("cells_local", C.c_longlong),
         ("cells_global", C.c_longlong), ("steps_done", C.c_longlong), ("kernel_launches", C.c_longlong),
         ("device_bytes", C.c_longlong), ("plain_step_ms", C.c_double), ("plain_step_iterations", C.c_longlong),
+        ("pair_enabled", C.c_int),
     ]
 
 
@@ -97,6 +98,10 @@ def load_library(path=None):
     L.lbm_get_f.argtypes = [vp, dp]
     L.lbm_set_f.argtypes = [vp, dp, dp]
     L.lbm_macrovars.argtypes = [vp, dp, dp, dp, dp, dp]
+    L.lbm_set_f_async.argtypes = [vp, dp, dp]
+    L.lbm_set_f_commit.argtypes = [vp]
+    L.lbm_macrovars_async.argtypes = [vp, dp, dp, dp, dp, dp]
+    L.lbm_io_wait.argtypes = [vp]
     L.lbm_sync.argtypes = [vp]
     L.lbm_get_info.argtypes = [vp, C.POINTER(LbmInfo)]
     L.lbm_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
@@ -104,7 +109,7 @@ def load_library(path=None):
     L.lbm_last_error.restype = C.c_char_p
     L.lbm_version.restype = C.c_char_p
     for name in ("lbm_nccl_unique_id", "lbm_create", "lbm_peer_export", "lbm_peer_connect", "lbm_step", "lbm_step_timed", "lbm_timer_start", "lbm_timer_stop",
-                 "lbm_residual", "lbm_get_f",
+                 "lbm_residual", "lbm_get_f", "lbm_set_f_async", "lbm_set_f_commit", "lbm_macrovars_async", "lbm_io_wait",
                  "lbm_set_f", "lbm_macrovars", "lbm_sync", "lbm_get_info", "lbm_set_option", "lbm_destroy"):
         getattr(L, name).restype = C.c_int
     if path == LIB_PATH:
@@ -222,6 +227,19 @@ class Cavity3D:
 
     def raw_set_f(self, f_ptr, f_prev_ptr=None):
         _check(self._L.lbm_set_f(self._h, C.c_void_p(f_ptr), C.c_void_p(f_prev_ptr) if f_prev_ptr else None))
+
+    # pipelined host I/O (pinned host buffers given as raw addresses)
+    def raw_set_f_async(self, f_ptr, f_prev_ptr=None):
+        _check(self._L.lbm_set_f_async(self._h, C.c_void_p(f_ptr), C.c_void_p(f_prev_ptr) if f_prev_ptr else None))
+
+    def set_f_commit(self):
+        _check(self._L.lbm_set_f_commit(self._h))
+
+    def raw_macrovars_async(self, ptrs):
+        _check(self._L.lbm_macrovars_async(self._h, *[C.c_void_p(p) if p else None for p in ptrs]))
+
+    def io_wait(self):
+        _check(self._L.lbm_io_wait(self._h))
 
     def raw_macrovars(self, ptrs):
         _check(self._L.lbm_macrovars(self._h, *[C.c_void_p(p) if p else None for p in ptrs]))

@@ -5,8 +5,11 @@
 // t % SIDE_DEPTH and reads the slot iteration t-2 wrote.  Depth 4 (not 3) so that the two fused
 // iterations of k_step_pair read {t+2, t+3} and write {t, t+1}: disjoint (lbm3d_pair.cuh).
 static const int SIDE_DEPTH = 4;
-static double *side_slot(const lbm_ctx *c, long long t) {
-    return c->side + (t % SIDE_DEPTH) * ((long long)c->nzl * c->N);
+// Each slot has one ghost row below and above the slab ([nzl+2][N]): on several GPUs k_step_pair
+// recomputes the first iteration on the neighbours' boundary planes and needs their history there.
+static long long side_slot_elems(const lbm_ctx *c) { return (long long)(c->nzl + 2) * c->N; }
+static double *side_slot(const lbm_ctx *c, long long t) {   // -> row of local plane 0
+    return c->side + (((t % SIDE_DEPTH) + SIDE_DEPTH) % SIDE_DEPTH) * side_slot_elems(c) + c->N;
 }
 
 static void choose_block(const lbm_ctx *c, dim3 *blk, dim3 *grd_xy) {
@@ -49,7 +52,7 @@ static lbm3d::KP make_kp(const lbm_ctx *c) {
     p.N = c->N; p.M = c->N - 1; p.Mz = c->N - 1;
     p.nzl = c->nzl; p.k0 = c->k0;
     p.kl0 = 0; p.kstride = 1; p.partial_base = 0;
-    p.G = c->G; p.zlo = 0; p.zhi = c->nzl; p.Lz = c->nzl;
+    p.G = c->G; p.zlo = 0; p.zhi = c->nzl; p.Lz = c->nzl; p.nseg1 = 1 << 30; p.zlo2 = 0; p.zhi2 = 0;
     p.N2 = c->N2; p.PS = c->PS; p.FS = c->FS;
     p.omega = c->OMEGA; p.omegam = c->OMEGAm; p.omomega = c->OmOMEGA; p.gammainv = c->gammainv;
     p.ulid = c->ulid; p.vlid = c->vlid; p.wlid = c->wlid;
@@ -118,20 +121,22 @@ static void launch_step(lbm_ctx *c, int mode, const lbm3d::KP &p, dim3 grid, dim
     }
 }
 
+static int halo_exchange(lbm_ctx *c, double *L, cudaStream_t st, bool deep, long long next_t);
+
 // ---- two iterations per pass (lbm3d_pair.cuh) -------------------------------------------------------
-template <int TY, int MINB, bool PIPE>
+template <int TY, int MINB, int STAGE>
 static int launch_pair_v(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, cudaStream_t st) {
     const bool g1 = (c->prm.GAMMA == 1.0);
     const dim3 blk(lbm3d::PAIR_TX, TY, 1);
-    const int smem = lbm3d::pair_smem_bytes(TY);
+    const int smem = lbm3d::pair_smem_bytes(TY, STAGE);
 #define LBM_PAIR_LAUNCH(M_, G_)                                                                              \
     do {                                                                                                     \
         static bool attr_done[16] = {false};                                                                 \
         if (!attr_done[c->dev & 15]) {                                                                       \
-            CK(cudaFuncSetAttribute(lbm3d::k_step_pair<M_, G_, TY, MINB, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            CK(cudaFuncSetAttribute(lbm3d::k_step_pair<M_, G_, TY, MINB, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
             attr_done[c->dev & 15] = true;                                                                   \
         }                                                                                                    \
-        lbm3d::k_step_pair<M_, G_, TY, MINB, PIPE><<<grid, blk, smem, st>>>(p);                              \
+        lbm3d::k_step_pair<M_, G_, TY, MINB, STAGE><<<grid, blk, smem, st>>>(p);                              \
     } while (0)
     if (c->prm.METHOD == 1) {
         if (g1) LBM_PAIR_LAUNCH(1, true); else LBM_PAIR_LAUNCH(1, false);
@@ -143,11 +148,11 @@ static int launch_pair_v(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, cudaStream_t
     return LBM_OK;
 }
 
-// Tile variants: rows per block, resident blocks per SM, register pipelining (lbm3d_pair.cuh).
-struct PairVariant { int ty, minb, pipe; };
-static const PairVariant PAIR_VARIANTS[] = {{20, 1, 0}, {16, 1, 1}, {10, 2, 0}, {16, 1, 0}, {18, 1, 0}, {8, 2, 1}};
+// Tile variants: rows per block, resident blocks per SM, staging mode (lbm3d_pair.cuh).
+struct PairVariant { int ty, minb, stage; };
+static const PairVariant PAIR_VARIANTS[] = {{20, 1, 0}, {16, 1, 2}, {10, 2, 0}, {16, 1, 0}, {16, 1, 1}, {17, 1, 1}, {12, 1, 1}, {10, 2, 3}};
 static const int PAIR_NVARIANTS = (int)(sizeof(PAIR_VARIANTS) / sizeof(PAIR_VARIANTS[0]));
-static const int PAIR_DEFAULT_VARIANT = 0;
+static const int PAIR_DEFAULT_VARIANT = 7;   // 2 blocks of 32 x 10 per SM, no prefetch: best of profiles/r02_pair_ab.md
 
 static int pair_variant(const lbm_ctx *c) {
     return (c->pair_variant >= 0 && c->pair_variant < PAIR_NVARIANTS) ? c->pair_variant : PAIR_DEFAULT_VARIANT;
@@ -156,35 +161,66 @@ static int pair_ty(const lbm_ctx *c) { return PAIR_VARIANTS[pair_variant(c)].ty;
 
 static int launch_pair(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, cudaStream_t st) {
     switch (pair_variant(c)) {
-        case 0: return launch_pair_v<20, 1, false>(c, p, grid, st);
-        case 1: return launch_pair_v<16, 1, true>(c, p, grid, st);
-        case 2: return launch_pair_v<10, 2, false>(c, p, grid, st);
-        case 3: return launch_pair_v<16, 1, false>(c, p, grid, st);
-        case 4: return launch_pair_v<18, 1, false>(c, p, grid, st);
-        default: return launch_pair_v<8, 2, true>(c, p, grid, st);
+        case 0: return launch_pair_v<20, 1, 0>(c, p, grid, st);
+        case 1: return launch_pair_v<16, 1, 2>(c, p, grid, st);
+        case 2: return launch_pair_v<10, 2, 0>(c, p, grid, st);
+        case 3: return launch_pair_v<16, 1, 0>(c, p, grid, st);
+        case 4: return launch_pair_v<16, 1, 1>(c, p, grid, st);
+        case 5: return launch_pair_v<17, 1, 1>(c, p, grid, st);
+        case 6: return launch_pair_v<12, 1, 1>(c, p, grid, st);
+        default: return launch_pair_v<10, 2, 3>(c, p, grid, st);
     }
 }
 
 static bool pair_enabled(const lbm_ctx *c) {
-    if (c->prm.dim != 3 || c->prm.nranks != 1) return false;
+    if (c->prm.dim != 3) return false;
+    if (c->prm.nranks > 1 && (c->p2p || c->nzl < 4 || c->G < 2)) return false;   // the fused direct halo is single-step only
     if (c->pair >= 0) return c->pair != 0;
-    return false;
+    // automatic: HBM-resident slabs (>= 128^3 cells per GPU); below that the step is launch-bound and
+    // the CUDA-graph / direct-halo paths of the single-step kernel win
+    return c->FS >= (1LL << 21);
 }
 
 // Iterations t = steps and t+1 in ONE pass: reads lat[cur] = S(t-1), writes lat[cur^1] = S(t+1).
 static int run_pair(lbm_ctx *c) {
     lbm3d::KP p = make_kp(c);
     const long long t = c->steps;
-    kp_set_lattices(c, &p, c->lat[c->cur], c->lat[c->cur ^ 1]);
+    const int dsti = c->cur ^ 1;
+    kp_set_lattices(c, &p, c->lat[c->cur], c->lat[dsti]);
     p.side_rd = side_slot(c, t + 2);  p.side_wr = side_slot(c, t);
     p.side_rd2 = side_slot(c, t + 3); p.side_wr2 = side_slot(c, t + 1);
-    p.zlo = 0; p.zhi = c->nzl;
-    p.Lz = c->pair_lz > 0 ? c->pair_lz : 64;
-    if (p.Lz > c->nzl) p.Lz = c->nzl;
     const int ty = pair_ty(c);
-    const dim3 grid((c->N + lbm3d::PAIR_OX - 1) / lbm3d::PAIR_OX, (c->N + ty - 3) / (ty - 2), (c->nzl + p.Lz - 1) / p.Lz);
-    int rc = launch_pair(c, p, grid, c->s_main);
-    if (rc) return rc;
+    const unsigned gx = (c->N + lbm3d::PAIR_OX - 1) / lbm3d::PAIR_OX, gy = (c->N + ty - 3) / (ty - 2);
+    int Lz = c->pair_lz > 0 ? c->pair_lz : 32;
+    int rc;
+    if (c->prm.nranks == 1) {
+        p.zlo = 0; p.zhi = c->nzl;
+        p.Lz = Lz < c->nzl ? Lz : c->nzl;
+        if ((rc = launch_pair(c, p, dim3(gx, gy, (c->nzl + p.Lz - 1) / p.Lz), c->s_main))) return rc;
+    } else {
+        // Same two-stream schedule as run_iteration: s_halo (high priority) computes the two output
+        // planes at each end of the slab -- everything the neighbours need -- and then exchanges
+        // them; s_main computes the planes in between, concurrently.
+        //   interior(s) reads planes [0, nzl) and writes [2, nzl-2): needs boundary(s-1);
+        //   boundary(s) reads planes [-2, 4) + [nzl-4, nzl+2) and writes [0,2) + [nzl-2,nzl): needs
+        //               interior(s-1) and the exchange of step s-1 (stream order on s_halo).
+        CK(cudaStreamWaitEvent(c->s_main, c->ev_bnd, 0));
+        CK(cudaEventRecord(c->ev_main, c->s_main));
+        CK(cudaStreamWaitEvent(c->s_halo, c->ev_main, 0));
+        p.Lz = 2; p.zlo = 0; p.zhi = 2; p.nseg1 = 1; p.zlo2 = c->nzl - 2; p.zhi2 = c->nzl;
+        if ((rc = launch_pair(c, p, dim3(gx, gy, 2), c->s_halo))) return rc;
+        CK(cudaEventRecord(c->ev_bnd, c->s_halo));
+        if ((rc = halo_exchange(c, c->lat[dsti], c->s_halo, true, t + 2))) return rc;
+        CK(cudaEventRecord(c->ev_halo, c->s_halo));
+        c->halo_pending = true;
+        const int zi = c->nzl - 4;   // interior output planes [2, nzl-2)
+        if (zi > 0) {
+            p.zlo = 2; p.zhi = c->nzl - 2; p.nseg1 = 1 << 30;
+            const int nseg = (zi + Lz - 1) / Lz;
+            p.Lz = (zi + nseg - 1) / nseg;   // equal segments
+            if ((rc = launch_pair(c, p, dim3(gx, gy, nseg), c->s_main))) return rc;
+        }
+    }
     CK(cudaGetLastError());
     c->cur ^= 1;
     c->steps += 2;
@@ -220,21 +256,55 @@ static int ensure_partials(lbm_ctx *c) {
 // Exchange the face-crossing populations of lattice `L` (just written) with the z-neighbours.
 // Up-going populations (cz=+1) of my top plane -> bottom ghost of rank+1; down-going (cz=-1) of my
 // bottom plane -> top ghost of rank-1.  Each is one contiguous N^2 block (z is the slowest axis, 3D:48).
-static int halo_exchange(lbm_ctx *c, double *L, cudaStream_t st) {
-    const int r = c->prm.rank, P = c->prm.nranks;
+//
+// `deep` (two-iterations-per-pass stepping): the next kernel recomputes the first of its two
+// iterations on the neighbours' boundary planes, so two ghost planes per side are filled -- the
+// outer one with the 5 populations that enter the inner one, the inner one with those 5 plus the
+// 9 in-plane populations (19 planes per face and direction instead of 5, once per TWO iterations)
+// -- and the x = N-1 stale-f14 row of the slot that kernel reads.
+static const int Q_IN[9] = {0, 1, 2, 3, 4, 7, 8, 13, 14};   // cz = 0
+static int halo_exchange(lbm_ctx *c, double *L, cudaStream_t st, bool deep, long long next_t) {
+    const int r = c->prm.rank, P = c->prm.nranks, G = c->G;
     const size_t n = (size_t)c->N2;
+    const long long PS = c->PS, N2 = c->N2, nzl = c->nzl;
+#define PLANE(q, kl) (L + (long long)(q) * PS + ((long long)(kl) + G) * N2)
     NK(g_nccl.GroupStart());
-    for (int a = 0; a < 5; a++) {
-        if (r + 1 < P) {
-            NK(g_nccl.Send(L + (long long)Q_UP[a] * c->PS + (long long)c->nzl * c->N2, n, ncclDouble, r + 1, c->comm, st));
-            NK(g_nccl.Recv(L + (long long)Q_DN[a] * c->PS + (long long)(c->nzl + 1) * c->N2, n, ncclDouble, r + 1, c->comm, st));
+    if (!deep) {
+        for (int a = 0; a < 5; a++) {
+            if (r + 1 < P) {
+                NK(g_nccl.Send(PLANE(Q_UP[a], nzl - 1), n, ncclDouble, r + 1, c->comm, st));
+                NK(g_nccl.Recv(PLANE(Q_DN[a], nzl), n, ncclDouble, r + 1, c->comm, st));
+            }
+            if (r > 0) {
+                NK(g_nccl.Send(PLANE(Q_DN[a], 0), n, ncclDouble, r - 1, c->comm, st));
+                NK(g_nccl.Recv(PLANE(Q_UP[a], -1), n, ncclDouble, r - 1, c->comm, st));
+            }
+        }
+    } else {
+        double *side = side_slot(c, next_t - 2);   // the slot the first iteration of a pair starting at next_t reads
+        if (r + 1 < P) {   // my top two planes -> rank+1's bottom ghosts; its bottom two planes -> my top ghosts
+            for (int a = 0; a < 5; a++) NK(g_nccl.Send(PLANE(Q_UP[a], nzl - 2), n, ncclDouble, r + 1, c->comm, st));
+            for (int a = 0; a < 5; a++) NK(g_nccl.Send(PLANE(Q_UP[a], nzl - 1), n, ncclDouble, r + 1, c->comm, st));
+            for (int a = 0; a < 9; a++) NK(g_nccl.Send(PLANE(Q_IN[a], nzl - 1), n, ncclDouble, r + 1, c->comm, st));
+            NK(g_nccl.Send(side + (nzl - 1) * c->N, (size_t)c->N, ncclDouble, r + 1, c->comm, st));
+            for (int a = 0; a < 5; a++) NK(g_nccl.Recv(PLANE(Q_DN[a], nzl + 1), n, ncclDouble, r + 1, c->comm, st));
+            for (int a = 0; a < 5; a++) NK(g_nccl.Recv(PLANE(Q_DN[a], nzl), n, ncclDouble, r + 1, c->comm, st));
+            for (int a = 0; a < 9; a++) NK(g_nccl.Recv(PLANE(Q_IN[a], nzl), n, ncclDouble, r + 1, c->comm, st));
+            NK(g_nccl.Recv(side + nzl * c->N, (size_t)c->N, ncclDouble, r + 1, c->comm, st));
         }
         if (r > 0) {
-            NK(g_nccl.Send(L + (long long)Q_DN[a] * c->PS + (long long)1 * c->N2, n, ncclDouble, r - 1, c->comm, st));
-            NK(g_nccl.Recv(L + (long long)Q_UP[a] * c->PS + (long long)0 * c->N2, n, ncclDouble, r - 1, c->comm, st));
+            for (int a = 0; a < 5; a++) NK(g_nccl.Send(PLANE(Q_DN[a], 1), n, ncclDouble, r - 1, c->comm, st));
+            for (int a = 0; a < 5; a++) NK(g_nccl.Send(PLANE(Q_DN[a], 0), n, ncclDouble, r - 1, c->comm, st));
+            for (int a = 0; a < 9; a++) NK(g_nccl.Send(PLANE(Q_IN[a], 0), n, ncclDouble, r - 1, c->comm, st));
+            NK(g_nccl.Send(side, (size_t)c->N, ncclDouble, r - 1, c->comm, st));
+            for (int a = 0; a < 5; a++) NK(g_nccl.Recv(PLANE(Q_UP[a], -2), n, ncclDouble, r - 1, c->comm, st));
+            for (int a = 0; a < 5; a++) NK(g_nccl.Recv(PLANE(Q_UP[a], -1), n, ncclDouble, r - 1, c->comm, st));
+            for (int a = 0; a < 9; a++) NK(g_nccl.Recv(PLANE(Q_IN[a], -1), n, ncclDouble, r - 1, c->comm, st));
+            NK(g_nccl.Recv(side - c->N, (size_t)c->N, ncclDouble, r - 1, c->comm, st));
         }
     }
     NK(g_nccl.GroupEnd());
+#undef PLANE
     return LBM_OK;
 }
 
@@ -311,11 +381,14 @@ static int run_iteration(lbm_ctx *c, int mode) {
         CK(cudaStreamWaitEvent(c->s_halo, c->ev_main, 0));
         const int nb = c->nzl >= 2 ? 2 : 1;
         p.kl0 = 0; p.kstride = c->nzl >= 2 ? c->nzl - 1 : 1; p.partial_base = 0;
+        const bool deep = pair_enabled(c);   // the next step may be a fused pair: fill both ghost planes (halo_exchange)
         if (!c->p2p) {
             launch_step(c, mode, p, dim3(gxy.x, gxy.y, nb), blk, c->s_halo);
             CK(cudaEventRecord(c->ev_bnd, c->s_halo));
-            int rc = halo_exchange(c, c->lat[src_i ^ 1], c->s_halo);
-            if (rc) return rc;
+            if (!deep) {
+                int rc = halo_exchange(c, c->lat[src_i ^ 1], c->s_halo, false, t + 1);
+                if (rc) return rc;
+            }
         } else {
             // Direct NVLink halo: wait until both neighbours finished their boundary kernels of the
             // previous iteration (they filled my ghosts and are done reading the ghosts I overwrite
@@ -328,9 +401,9 @@ static int run_iteration(lbm_ctx *c, int mode) {
             c->launches++;
             const int dsti = src_i ^ 1;
             for (int a = 0; a < 5; a++) {
-                p.peer_dn[a] = r > 0 ? c->peer_lat[0][dsti] + (long long)Q_DN[a] * c->peer_PS[0] + (long long)(c->peer_nzl[0] + 1) * c->N2
+                p.peer_dn[a] = r > 0 ? c->peer_lat[0][dsti] + (long long)Q_DN[a] * c->peer_PS[0] + (long long)(c->peer_nzl[0] + c->G) * c->N2
                                      : nullptr;
-                p.peer_up[a] = r + 1 < P ? c->peer_lat[1][dsti] + (long long)Q_UP[a] * c->peer_PS[1] : nullptr;
+                p.peer_up[a] = r + 1 < P ? c->peer_lat[1][dsti] + (long long)Q_UP[a] * c->peer_PS[1] + (long long)(c->G - 1) * c->N2 : nullptr;
             }
             p.done_count = c->done_count;
             p.sig_dn = r > 0 ? c->peer_sig[0] + 1 : nullptr;      // I am the neighbour "above" rank-1
@@ -344,12 +417,20 @@ static int run_iteration(lbm_ctx *c, int mode) {
             }
             CK(cudaEventRecord(c->ev_bnd, c->s_halo));
         }
-        CK(cudaEventRecord(c->ev_halo, c->s_halo));
-        c->halo_pending = true;
         if (c->nzl > 2) {
             p.kl0 = 1; p.kstride = 1; p.partial_base = (int)(bpp * nb);
             launch_step(c, mode, p, dim3(gxy.x, gxy.y, c->nzl - 2), blk, c->s_main);
         }
+        if (deep && !c->p2p) {
+            // the deep exchange also ships planes 1 and nzl-2, which the interior launch computed:
+            // no overlap for the (rare) single steps between fused pairs
+            CK(cudaEventRecord(c->ev_int, c->s_main));
+            CK(cudaStreamWaitEvent(c->s_halo, c->ev_int, 0));
+            int rc = halo_exchange(c, c->lat[src_i ^ 1], c->s_halo, true, t + 1);
+            if (rc) return rc;
+        }
+        CK(cudaEventRecord(c->ev_halo, c->s_halo));
+        c->halo_pending = true;
         if (mode == lbm3d::MODE_STEP_DIFF_STOREF) CK(cudaStreamWaitEvent(c->s_main, c->ev_bnd, 0));  // its block partials
     }
     CK(cudaGetLastError());

@@ -69,6 +69,7 @@ struct KP {
     int kl0, kstride;    // this launch covers local planes kl0 + blockIdx.z * kstride
     int G;               // ghost planes below local plane 0 (cell = (kl+G)*N^2 + j*N + i)
     int zlo, zhi, Lz;    // k_step_pair: output planes [zlo, zhi) of this launch, planes per z segment
+    int nseg1, zlo2, zhi2;  // ... blocks with blockIdx.z >= nseg1 cover a second range [zlo2, zhi2) (slab-boundary launch)
     int partial_base;    // offset of this launch's block partials
     long long N2, PS, FS;
     double omega, omegam, omomega, gammainv;   // 3D:21,23,30,40

@@ -34,24 +34,30 @@ namespace lbm3d {
 constexpr int PAIR_TX = 32;       // threads per tile row (one warp)
 constexpr int PAIR_OX = 30;       // output cells per tile row
 
-__host__ __device__ constexpr int pair_smem_bytes(int TY) { return 32 * PAIR_TX * TY * (int)sizeof(double); }
+__host__ __device__ constexpr int pair_smem_bytes(int TY, int STAGE) { return (32 + (STAGE == 1 ? 19 : 0)) * PAIR_TX * TY * (int)sizeof(double); }
 
 #define LBM_PREFETCH_L2(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))
 
 // Variants (template parameters, A/B'd on the GPU, profiles/r02_pair_ab.md):
 //   MINB  resident blocks per SM the register budget is sized for (1: big tiles; 2: two smaller blocks
 //         whose load and compute phases interleave);
-//   PIPE  software pipelining through registers: the 19 pulls of plane pz+1 are issued right after
-//         the first barrier and stay in flight while step B computes, so step A never waits for HBM.
+//   STAGE 0: step A pulls straight from HBM/L2 into registers (L2 prefetch one plane ahead);
+//         1: the 19 pulls of plane pz+1 are issued as asynchronous copies (cp.async, LDGSTS) into a
+//            per-thread staging slot of shared memory right after the first barrier and land while
+//            step B computes, so step A never waits for HBM (costs 152 B of shared memory per cell);
+//         2: like 0 but software-pipelined through 19 extra registers (slower: 128 registers leave
+//            16 warps per SM and the pulls still stall -- kept for the record, profiles/r02_pair_ab.md).
 //
 // grid = (ceil(N/30), ceil(N/(TY-2)), ceil((zhi-zlo)/Lz)); block = (32, TY); dynamic smem = pair_smem_bytes(TY).
-template <int METHOD, bool G1, int TY, int MINB, bool PIPE>
+template <int METHOD, bool G1, int TY, int MINB, int STAGE>
 __global__ void __launch_bounds__(PAIR_TX *TY, MINB) k_step_pair(const __grid_constant__ KP p) {
     extern __shared__ double sm[];
     constexpr int NT = PAIR_TX * TY;
     double *const s_up = sm;             // [3 planes][4][NT]   populations 9, 11, 16, 18
     double *const s_in = sm + 12 * NT;   // [2 planes][8][NT]   populations 1, 2, 3, 4, 7, 8, 13, 14
     double *const s_dn = sm + 28 * NT;   // [4][NT]             populations 10, 12, 15, 17
+    double *const s_st = sm + 32 * NT;   // [19][NT]            STAGE 1: this thread's pulls of the next plane
+    constexpr bool PIPE = (STAGE == 2);
 
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int li = ty * PAIR_TX + tx;
@@ -60,8 +66,10 @@ __global__ void __launch_bounds__(PAIR_TX *TY, MINB) k_step_pair(const __grid_co
     const int N1 = p.N;
     const bool in_box = (i >= 0) && (i < N1) && (j >= 0) && (j < N1);
     const bool out_cell = in_box && (tx >= 1) && (tx <= PAIR_OX) && (ty >= 1) && (ty <= TY - 2);
-    const int z0 = p.zlo + (int)blockIdx.z * p.Lz;
-    const int z1 = min(z0 + p.Lz, p.zhi);
+    int zb = (int)blockIdx.z, zlo = p.zlo, zhi = p.zhi;
+    if (zb >= p.nseg1) { zb -= p.nseg1; zlo = p.zlo2; zhi = p.zhi2; }   // second z range of a slab-boundary launch
+    const int z0 = zlo + zb * p.Lz;
+    const int z1 = min(z0 + p.Lz, zhi);
     const int bx = (i == 0) ? 1 : ((i == p.M) ? 2 : 0);
     const int by = (j == 0) ? 1 : ((j == p.M) ? 2 : 0);
     const int rowcell = j * N1 + i;
@@ -73,9 +81,19 @@ __global__ void __launch_bounds__(PAIR_TX *TY, MINB) k_step_pair(const __grid_co
 
 #define LBM_PULL_INTO(arr, at) { _Pragma("unroll") for (int q_ = 0; q_ < Q; q_++) arr[q_] = lbm_load(p.srcq[q_] + (at)); }
 #define LBM_PLANE_IN_BOX(z) ((z) + p.k0 >= 0 && (z) + p.k0 <= p.Mz)
+#define LBM_STAGE_PLANE(at)                                                                                         \
+    {                                                                                                               \
+        const unsigned dst_ = (unsigned)__cvta_generic_to_shared(s_st + li);                                        \
+        _Pragma("unroll") for (int q_ = 0; q_ < Q; q_++)                                                            \
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_ + q_ * NT * 8), "l"(p.srcq[q_] + (at)) : "memory"); \
+    }
     double fn[Q];                              // PIPE: the pulls of the next plane, in flight
     if (PIPE) {
         if (in_box && LBM_PLANE_IN_BOX(z0 - 1)) LBM_PULL_INTO(fn, cell)
+    }
+    if (STAGE == 1) {
+        if (in_box && LBM_PLANE_IN_BOX(z0 - 1)) LBM_STAGE_PLANE(cell)
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
     for (int pz = z0 - 1; pz <= z1; pz++, cell += N2i) {
@@ -88,6 +106,10 @@ __global__ void __launch_bounds__(PAIR_TX *TY, MINB) k_step_pair(const __grid_co
             if (PIPE) {
 #pragma unroll
                 for (int q = 0; q < Q; q++) f[q] = fn[q];
+            } else if (STAGE == 1) {
+                asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+                for (int q = 0; q < Q; q++) f[q] = s_st[q * NT + li];   // this thread's own copies: no barrier needed
             } else {
                 LBM_PULL_INTO(f, cell)
             }
@@ -119,9 +141,13 @@ __global__ void __launch_bounds__(PAIR_TX *TY, MINB) k_step_pair(const __grid_co
             // pulls of the next plane: in flight while step B computes
             if (in_box && pz < z1 && LBM_PLANE_IN_BOX(pz + 1)) LBM_PULL_INTO(fn, cell + N2i)
         }
+        if (STAGE == 1) {
+            if (in_box && pz < z1 && LBM_PLANE_IN_BOX(pz + 1)) LBM_STAGE_PLANE(cell + N2i)
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         // Warm L2 with the lines a later step A pulls (every (population, plane) pair is read exactly
         // once per block, so without this every pull is a DRAM-latency miss).
-        if (in_box && pz + (PIPE ? 1 : 0) < z1) {
+        if (STAGE != 1 && STAGE != 3 && in_box && pz + (PIPE ? 1 : 0) < z1) {   // STAGE 3: variant 0 without the prefetch (A/B only)
             const int ahead = cell + (PIPE ? 2 : 1) * N2i;
 #define LBM_PF(q, cx, cy, cz, wq) LBM_PREFETCH_L2(p.srcq[q] + ahead);
             LBM_D3Q19_VEL(LBM_PF)
@@ -169,6 +195,7 @@ __global__ void __launch_bounds__(PAIR_TX *TY, MINB) k_step_pair(const __grid_co
         __syncthreads();
     }
 #undef LBM_PULL_INTO
+#undef LBM_STAGE_PLANE
 #undef LBM_PLANE_IN_BOX
 }
 

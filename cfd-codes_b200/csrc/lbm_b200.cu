@@ -81,12 +81,19 @@ int lbm_destroy(lbm_ctx *c) {
     cudaFree(c->lat_alloc[0]); cudaFree(c->lat_alloc[1]); cudaFree(c->Fbuf); cudaFree(c->side);
     cudaFree(c->partials); cudaFree(c->d_red); cudaFree(c->d_flag);
     for (int a = 0; a < 5; a++) cudaFree(c->d_out[a]);
+    cudaFree(c->Fstage); cudaFree(c->side_stage);
+    if (c->ev_up) cudaEventDestroy(c->ev_up);
+    if (c->ev_mv) cudaEventDestroy(c->ev_mv);
+    if (c->ev_down) cudaEventDestroy(c->ev_down);
+    if (c->ev_commit) cudaEventDestroy(c->ev_commit);
+    if (c->s_copy) { cudaStreamSynchronize(c->s_copy); cudaStreamDestroy(c->s_copy); }
     cudaFree(c->u2); cudaFree(c->v2); cudaFree(c->rho2);
     for (int a = 0; a < 3; a++) cudaFree(c->out2[a]);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->ev_int) cudaEventDestroy(c->ev_int);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     drop_graphs(c);
@@ -106,7 +113,7 @@ static int create3d(lbm_ctx *c) {
     c->k1 = (int)((long long)(p.rank + 1) * p.N / p.nranks);
     c->nzl = c->k1 - c->k0;
     if (c->nzl < 1) return fail(LBM_ERR_INVALID, "rank %d of %d owns no plane of N=%d", p.rank, p.nranks, p.N);
-    c->G = 1;
+    c->G = p.nranks > 1 ? 2 : 1;   // two ghost planes per side on several GPUs (k_step_pair recomputes one plane of iteration t)
     c->PS = (long long)(c->nzl + 2 * c->G) * c->N2;
     c->FS = (long long)c->nzl * c->N2;
     if (c->PS >= (1LL << 31)) return fail(LBM_ERR_INVALID, "more than 2^31 cells per GPU");
@@ -137,7 +144,7 @@ static int create3d(lbm_ctx *c) {
         CK(cudaMemsetAsync(c->lat_alloc[l] + c->pad + (long long)lbm3d::Q * c->PS, 0, (size_t)c->pad * sizeof(double), c->s_main));
         c->lat[l] = c->lat_alloc[l] + c->pad;
     }
-    const long long side_n = (long long)c->nzl * c->N;
+    const long long side_n = side_slot_elems(c);
     if ((rc = dev_alloc(c, &c->side, SIDE_DEPTH * side_n))) return rc;
     if ((rc = dev_alloc(c, &c->d_red, 2))) return rc;
     if ((rc = dev_alloc(c, &c->d_flag, 1))) return rc;
@@ -230,6 +237,7 @@ int lbm_create(const lbm_params *p, lbm_ctx **out) {
         CKD(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
         CKD(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
         CKD(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+        CKD(cudaEventCreateWithFlags(&c->ev_int, cudaEventDisableTiming));
         if ((rc = nccl_load())) { lbm_destroy(c); return rc; }
         ncclUniqueId id;
         memcpy(&id, p->nccl_id, LBM_NCCL_ID_BYTES);
@@ -435,42 +443,70 @@ int lbm_get_f(lbm_ctx *c, double *host_full) {
     return LBM_OK;
 }
 
-int lbm_set_f(lbm_ctx *c, const double *host_f, const double *host_f_prev) {
+// ---- host <-> device state transfer ----------------------------------------------------------------
+// Uploads go through a second device buffer (`Fstage`) on a dedicated copy stream, downloads of the
+// macroscopic fields likewise, so that a host which processes a SEQUENCE of states can overlap the PCIe
+// traffic of batch k+1 / k-1 with the iterations of batch k:
+//     lbm_set_f_async(next)  ||  lbm_step(...), lbm_residual(...)   then   lbm_macrovars_async(out)
+// lbm_set_f / lbm_macrovars are the same operations followed by a wait.
+static int ensure_copy_stream(lbm_ctx *c) {
+    if (c->s_copy) return LBM_OK;
+    CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_mv, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_down, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_commit, cudaEventDisableTiming));
+    return LBM_OK;
+}
+
+int lbm_set_f_async(lbm_ctx *c, const double *host_f, const double *host_f_prev) {
     if (!c || !host_f) return fail(LBM_ERR_INVALID, "null argument");
+    if (c->prm.dim != 3) return fail(LBM_ERR_INVALID, "lbm_set_f_async: dim=3 only (use lbm_set_f)");
     CK(cudaSetDevice(c->dev));
-    if (c->prm.dim == 2) {
-        if (c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
-        int rc2 = copy_dist2d(c, const_cast<double *>(host_f), false);
-        if (rc2) return rc2;
-        if (c->prm.nranks > 1) { if ((rc2 = halo_exchange2d(c, c->lat[c->cur], c->s_main))) return rc2; CK(cudaStreamSynchronize(c->s_main)); }
-        return LBM_OK;
-    }
-    int rc = ensure_Fbuf(c);
+    int rc = ensure_copy_stream(c);
     if (rc) return rc;
-    if (c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
+    if (!c->Fstage && (rc = dev_alloc(c, &c->Fstage, (long long)lbm3d::Q * c->FS))) return rc;
+    if (!c->side_stage && (rc = dev_alloc(c, &c->side_stage, (long long)c->nzl * c->N))) return rc;
+    if (c->stage_commit_pending) {   // the previous commit still reads Fstage's predecessor: order after it
+        CK(cudaStreamWaitEvent(c->s_copy, c->ev_commit, 0));
+        c->stage_commit_pending = false;
+    }
     const long long N3 = c->host_local ? c->FS : c->N2 * c->N;
     const long long hk0 = c->host_local ? 0 : c->k0;
     for (int q = 0; q < lbm3d::Q; q++)
-        CK(cudaMemcpyAsync(c->Fbuf + (long long)q * c->FS, host_f + (long long)q * N3 + hk0 * c->N2,
-                           (size_t)c->FS * sizeof(double), cudaMemcpyHostToDevice, c->s_main));
+        CK(cudaMemcpyAsync(c->Fstage + (long long)q * c->FS, host_f + (long long)q * N3 + hk0 * c->N2,
+                           (size_t)c->FS * sizeof(double), cudaMemcpyHostToDevice, c->s_copy));
+    c->stage_has_prev = host_f_prev != nullptr;
+    if (host_f_prev)   // only the x = N-1 column of population 14 is needed from the other buffer (3D:421)
+        CK(cudaMemcpy2DAsync(c->side_stage, sizeof(double), host_f_prev + 14LL * N3 + hk0 * c->N2 + (c->N - 1),
+                             (size_t)c->N * sizeof(double), sizeof(double), (size_t)c->nzl * c->N, cudaMemcpyHostToDevice,
+                             c->s_copy));
+    CK(cudaEventRecord(c->ev_up, c->s_copy));
+    c->stage_ready = true;
+    return LBM_OK;
+}
+
+int lbm_set_f_commit(lbm_ctx *c) {
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    if (!c->stage_ready) return fail(LBM_ERR_INVALID, "lbm_set_f_commit without lbm_set_f_async");
+    CK(cudaSetDevice(c->dev));
+    if (c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
+    CK(cudaStreamWaitEvent(c->s_main, c->ev_up, 0));
+    // the uploaded state becomes the F buffer; the old F buffer becomes the next staging area
+    double *t = c->Fbuf; c->Fbuf = c->Fstage; c->Fstage = t;
+    c->stage_ready = false;
     // Stale f14 of the x = N-1 face (3D:421): iteration t = steps reads the slot iteration t-2 wrote --
-    // that value lives in the reference's OTHER buffer (host_f_prev) -- and iteration t+1 reads what
-    // t-1 wrote: this state's own post-BC f14.  The latter is gathered on the device from the uploaded
-    // F buffer; the former is one strided copy of the column (no host staging, no extra sync).
-    {
-        const long long side_n = (long long)c->nzl * c->N;
-        const unsigned gb = (unsigned)((side_n + 255) / 256);
-        lbm3d::k_gather_xmax<<<gb, 256, 0, c->s_main>>>(c->Fbuf + 14LL * c->FS, c->N, side_n, side_slot(c, c->steps + 3));
+    // that value lives in the reference's OTHER buffer (f_prev) -- and iteration t+1 reads what t-1
+    // wrote: this state's own post-BC f14, gathered on the device from the uploaded F buffer.
+    const long long side_n = (long long)c->nzl * c->N;
+    const unsigned gb = (unsigned)((side_n + 255) / 256);
+    lbm3d::k_gather_xmax<<<gb, 256, 0, c->s_main>>>(c->Fbuf + 14LL * c->FS, c->N, side_n, side_slot(c, c->steps + 3));
+    c->launches++;
+    if (c->stage_has_prev) {
+        CK(cudaMemcpyAsync(side_slot(c, c->steps + 2), c->side_stage, (size_t)side_n * sizeof(double), cudaMemcpyDeviceToDevice, c->s_main));
+    } else {
+        lbm3d::k_gather_xmax<<<gb, 256, 0, c->s_main>>>(c->Fbuf + 14LL * c->FS, c->N, side_n, side_slot(c, c->steps + 2));
         c->launches++;
-        if (host_f_prev) {
-            CK(cudaMemcpy2DAsync(side_slot(c, c->steps + 2), sizeof(double),
-                                 host_f_prev + 14LL * N3 + hk0 * c->N2 + (c->N - 1), (size_t)c->N * sizeof(double),
-                                 sizeof(double), (size_t)side_n, cudaMemcpyHostToDevice, c->s_main));
-        } else {
-            lbm3d::k_gather_xmax<<<gb, 256, 0, c->s_main>>>(c->Fbuf + 14LL * c->FS, c->N, side_n, side_slot(c, c->steps + 2));
-            c->launches++;
-        }
-        CK(cudaGetLastError());
     }
     // S = collide(F) into lat[cur]
     dim3 blk, gxy;
@@ -483,36 +519,83 @@ int lbm_set_f(lbm_ctx *c, const double *host_f, const double *host_f_prev) {
     c->launches++;
     CK(cudaGetLastError());
     if (c->prm.nranks > 1) {
-        rc = halo_exchange(c, c->lat[c->cur], c->s_main);
+        int rc = halo_exchange(c, c->lat[c->cur], c->s_main, pair_enabled(c), c->steps);
         if (rc) return rc;
+    }
+    if (c->Fstage) {   // the next upload overwrites the buffer that was Fbuf: everything queued so far may still read it
+        CK(cudaEventRecord(c->ev_commit, c->s_main));
+        c->stage_commit_pending = true;
     }
     c->f_valid = true;
     c->residual_ready = false;
+    return LBM_OK;
+}
+
+int lbm_set_f(lbm_ctx *c, const double *host_f, const double *host_f_prev) {
+    if (!c || !host_f) return fail(LBM_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->dev));
+    if (c->prm.dim == 2) {
+        if (c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
+        int rc2 = copy_dist2d(c, const_cast<double *>(host_f), false);
+        if (rc2) return rc2;
+        if (c->prm.nranks > 1) { if ((rc2 = halo_exchange2d(c, c->lat[c->cur], c->s_main))) return rc2; CK(cudaStreamSynchronize(c->s_main)); }
+        return LBM_OK;
+    }
+    int rc = ensure_Fbuf(c);
+    if (rc) return rc;
+    if ((rc = lbm_set_f_async(c, host_f, host_f_prev))) return rc;
+    if ((rc = lbm_set_f_commit(c))) return rc;
     CK(cudaStreamSynchronize(c->s_main));
+    return LBM_OK;
+}
+
+// k_macrovars on s_main, then the five field downloads on the copy stream.
+int lbm_macrovars_async(lbm_ctx *c, double *u1, double *u2, double *u3, double *rho, double *vmag) {
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    if (c->prm.dim != 3) return fail(LBM_ERR_INVALID, "lbm_macrovars_async: dim=3 only (use lbm_macrovars)");
+    CK(cudaSetDevice(c->dev));
+    int rc = ensure_copy_stream(c);
+    if (rc) return rc;
+    if (c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
+    if ((rc = materialise_F(c))) return rc;
+    double *host[5] = {u1, u2, u3, rho, vmag};
+    for (int a = 0; a < 5; a++)
+        if (!c->d_out[a]) { if ((rc = dev_alloc(c, &c->d_out[a], c->FS))) return rc; }
+    const long long n = c->FS;
+    if (c->down_pending) CK(cudaStreamWaitEvent(c->s_main, c->ev_down, 0));   // previous downloads still read d_out
+    lbm3d::k_macrovars<<<(unsigned)((n + 255) / 256), 256, 0, c->s_main>>>(c->Fbuf, c->FS, c->d_out[0], c->d_out[1],
+                                                                          c->d_out[2], c->d_out[3], c->d_out[4]);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev_mv, c->s_main));
+    CK(cudaStreamWaitEvent(c->s_copy, c->ev_mv, 0));
+    for (int a = 0; a < 5; a++)
+        if (host[a])
+            CK(cudaMemcpyAsync(host[a] + (c->host_local ? 0LL : (long long)c->k0 * c->N2), c->d_out[a], (size_t)n * sizeof(double),
+                               cudaMemcpyDeviceToHost, c->s_copy));
+    CK(cudaEventRecord(c->ev_down, c->s_copy));
+    c->down_pending = true;
+    return LBM_OK;
+}
+
+int lbm_io_wait(lbm_ctx *c) {
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->dev));
+    if (c->s_copy) CK(cudaStreamSynchronize(c->s_copy));
+    c->down_pending = false;
     return LBM_OK;
 }
 
 int lbm_macrovars(lbm_ctx *c, double *u1, double *u2, double *u3, double *rho, double *vmag) {
     if (!c) return fail(LBM_ERR_INVALID, "null context");
     CK(cudaSetDevice(c->dev));
-    if (c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
-    if (c->prm.dim == 2) return macrovars2d(c, u1, u2, rho, vmag);
-    int rc = materialise_F(c);
+    if (c->prm.dim == 2) {
+        if (c->halo_pending) { CK(cudaStreamWaitEvent(c->s_main, c->ev_halo, 0)); c->halo_pending = false; }
+        return macrovars2d(c, u1, u2, rho, vmag);
+    }
+    int rc = lbm_macrovars_async(c, u1, u2, u3, rho, vmag);
     if (rc) return rc;
-    double *host[5] = {u1, u2, u3, rho, vmag};
-    for (int a = 0; a < 5; a++)
-        if (!c->d_out[a]) { if ((rc = dev_alloc(c, &c->d_out[a], c->FS))) return rc; }
-    const long long n = c->FS;
-    lbm3d::k_macrovars<<<(unsigned)((n + 255) / 256), 256, 0, c->s_main>>>(c->Fbuf, c->FS, c->d_out[0], c->d_out[1],
-                                                                          c->d_out[2], c->d_out[3], c->d_out[4]);
-    c->launches++;
-    CK(cudaGetLastError());
-    for (int a = 0; a < 5; a++)
-        if (host[a])
-            CK(cudaMemcpyAsync(host[a] + (c->host_local ? 0LL : (long long)c->k0 * c->N2), c->d_out[a], (size_t)n * sizeof(double),
-                               cudaMemcpyDeviceToHost, c->s_main));
-    CK(cudaStreamSynchronize(c->s_main));
-    return LBM_OK;
+    return lbm_io_wait(c);
 }
 
 int lbm_get_info(lbm_ctx *c, lbm_info *o) {
@@ -526,6 +609,7 @@ int lbm_get_info(lbm_ctx *c, lbm_info *o) {
     cudaSetDevice(c->dev);
     resolve_spans(c, true);
     o->plain_step_ms = c->plain_ms; o->plain_step_iterations = c->plain_iters;
+    o->pair_enabled = (c->prm.dim == 3 && pair_enabled(c)) ? 1 : 0;
     return LBM_OK;
 }
 
@@ -558,7 +642,17 @@ int lbm_set_option(lbm_ctx *c, const char *key, long long value) {
             return fail(LBM_ERR_INVALID, "block_x*block_y > 256");
         }
     } else if (!strcmp(key, "pair")) {
+        const bool was = pair_enabled(c);
         c->pair = value < 0 ? -1 : (value != 0);
+        if (c->prm.nranks > 1 && pair_enabled(c) && !was) {
+            // Fused pairs read two ghost planes per side and the neighbours' stale-f14 rows: fill them
+            // now (on several GPUs switching `pair` on is therefore a COLLECTIVE call).
+            CK(cudaSetDevice(c->dev));
+            int rc = poll_flag(c);
+            if (rc) return rc;
+            if ((rc = halo_exchange(c, c->lat[c->cur], c->s_main, true, c->steps))) return rc;
+            CK(cudaStreamSynchronize(c->s_main));
+        }
         return LBM_OK;
     } else if (!strcmp(key, "pair_variant")) {
         if (value < -1 || value >= PAIR_NVARIANTS) return fail(LBM_ERR_INVALID, "pair_variant must be in [-1, %d)", PAIR_NVARIANTS);

@@ -76,9 +76,12 @@ static const int Q_DN[5] = {6, 10, 12, 15, 17};
 struct lbm_ctx {
     lbm_params prm;
     int dev = 0;
-    cudaStream_t s_main = nullptr, s_halo = nullptr;
+    cudaStream_t s_main = nullptr, s_halo = nullptr, s_copy = nullptr;   // s_copy: host<->device transfers (created on first use)
     bool own_main = false;
-    cudaEvent_t ev_bnd = nullptr, ev_halo = nullptr, ev_main = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_bnd = nullptr, ev_halo = nullptr, ev_main = nullptr, ev_int = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_up = nullptr, ev_mv = nullptr, ev_down = nullptr, ev_commit = nullptr;
+    double *Fstage = nullptr, *side_stage = nullptr;   // upload staging (lbm_set_f_async): [19][FS] and the f_prev column [nzl][N]
+    bool stage_ready = false, stage_has_prev = false, stage_commit_pending = false, down_pending = false;
     bool halo_pending = false;  // ev_halo has been recorded and not yet waited on by s_main
 
     int N = 0, nzl = 0, k0 = 0, k1 = 0;

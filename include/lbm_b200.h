@@ -73,6 +73,7 @@ typedef struct lbm_info {
     double plain_step_ms;         /* accumulated device time (CUDA events on the launching stream) of the
                                      iterations run by the plain step kernel inside lbm_step (dim=3) ... */
     long long plain_step_iterations; /* ... and how many iterations that covers */
+    int pair_enabled;             /* 1: plain iterations run two per pass over HBM (csrc/lbm3d_pair.cuh) */
 } lbm_info;
 
 /* Fills *p with the reference's defaults: dim=3, N=50, Re=100, UMAX=0.1, METHOD=1 (TRT), GAMMA=1,
@@ -126,10 +127,28 @@ int lbm_get_f(lbm_ctx *c, double *host_full);
  * overwritten), from which the never-streamed slot f14 at x = N-1 is taken (3D:421). */
 int lbm_set_f(lbm_ctx *c, const double *host_f, const double *host_f_prev);
 
+/* Asynchronous halves of lbm_set_f (dim=3), for hosts that feed a SEQUENCE of states and want the
+ * PCIe upload of the next state to overlap the iterations of the current one:
+ *   lbm_set_f_async  enqueues the host->device copies on the context's copy stream into a staging
+ *                    buffer and returns at once (host arrays: pinned memory, valid until the copy is
+ *                    done, i.e. until lbm_io_wait or the lbm_set_f_commit that follows has been
+ *                    waited on with lbm_sync);
+ *   lbm_set_f_commit makes the staged state the current one (stream-ordered after the upload;
+ *                    collective when nranks > 1, like lbm_set_f).
+ * lbm_set_f == lbm_set_f_async + lbm_set_f_commit + wait. */
+int lbm_set_f_async(lbm_ctx *c, const double *host_f, const double *host_f_prev);
+int lbm_set_f_commit(lbm_ctx *c);
+
 /* Replaces macrovars(f2) + calcvmag() (3D:365-366, 695-738): N^3 doubles each in LU3 order
  * (3D:47), this rank's planes only; any pointer may be NULL.  Velocities are divided by rho
  * (not multiplied by a reciprocal), as 3D:713-715. */
 int lbm_macrovars(lbm_ctx *c, double *u1, double *u2, double *u3, double *rho, double *vmag);
+
+/* lbm_macrovars without the final wait (dim=3): the fields are computed in stream order and
+ * downloaded on the copy stream; the host arrays are complete after lbm_io_wait. */
+int lbm_macrovars_async(lbm_ctx *c, double *u1, double *u2, double *u3, double *rho, double *vmag);
+/* Waits for the transfers queued by lbm_set_f_async / lbm_macrovars_async. */
+int lbm_io_wait(lbm_ctx *c);
 
 /* Waits for all work of the context and polls the negative-feq flag. */
 int lbm_sync(lbm_ctx *c);
@@ -137,7 +156,11 @@ int lbm_sync(lbm_ctx *c);
 int lbm_get_info(lbm_ctx *c, lbm_info *out);
 
 /* Options: "block_x" / "block_y" (thread-block shape of the step kernel), "track_residual" (0/1 at
- * run time), "host_local_layout" (1: the host arrays of lbm_get_f / lbm_set_f / lbm_macrovars are
+ * run time), "pair" (two iterations per pass over HBM, csrc/lbm3d_pair.cuh: -1 automatic, 0 off, 1 on;
+ * on several GPUs switching it on is a collective call), "pair_variant" / "pair_lz" (its tile variant
+ * and planes per z segment), "graphs" (CUDA-graph replay of launch-bound grids), "vec2", "halo_timeout_ms"
+ * (direct halo: how long a GPU waits for a neighbour before reporting an error; ranks must stay within
+ * that skew of each other, default 600 000), "host_local_layout" (1: the host arrays of lbm_get_f / lbm_set_f / lbm_macrovars are
  * compact local slabs [q][k1-k0][N][N] instead of full LU4 / LU3 arrays -- for multi-process runs
  * where no rank holds the whole field). */
 int lbm_set_option(lbm_ctx *c, const char *key, long long value);

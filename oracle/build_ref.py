@@ -97,6 +97,8 @@ CONFIGS_2D = [
     dict(N=100, M=300, Re="100", MAXITER="1E6", prntInt="1e3", THRESH="2E-9"),   # the reference's defaults (to convergence)
     dict(N=24, M=40, Re="40", MAXITER="200", prntInt="1", THRESH="0"),           # 200 iterations, state after the last one
     dict(N=17, M=23, Re="25", MAXITER="120", prntInt="1", THRESH="0"),           # odd sizes
+    # BASELINE config 5 grid for bench.py's cpu_baseline: 11 iterations, MLUPS printed at t = 5, 10; no output files
+    dict(N=8192, M=8192, Re="10000", MAXITER="11", prntInt="5", THRESH="0", SAVE="false"),
 ]
 
 
@@ -120,6 +122,8 @@ def build2d(cfg, force=False):
     subs = [(r"(const double Re = )[^;]+", cfg["Re"]), (r"(const int N = )[^;]+", str(cfg["N"])),
             (r"(const int M = )[^;]+", str(cfg["M"])), (r"(const double THRESH = )[^;]+", cfg["THRESH"]),
             (r"(const double MAXITER = )[^;]+", cfg["MAXITER"]), (r"(const int prntInt = )[^;]+", cfg["prntInt"])]
+    if "SAVE" in cfg:   # SAVE is one of the reference's own user parameters (2D:16)
+        subs.append((r"(const bool SAVE = )[^;]+", cfg["SAVE"]))
     for pat, val in subs:
         src, n = re.subn(pat, lambda m: m.group(1) + val, src, count=1)
         if n != 1:

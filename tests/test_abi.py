@@ -112,12 +112,13 @@ def test_fast_formatter_equals_printf(tmp_path):
 def test_step_kernel_resource_budget(lbm):
     """Performance invariants of the dominant kernel that can be checked without a GPU: the TRT step
     kernel must fit 5 blocks of 128 threads per SM (<= 102 registers, profiles/r01_ab_occupancy.log),
-    must not spill (no local-memory stack), and uses no shared memory."""
+    must not spill (no local-memory stack), and uses no shared memory of its own (cuobjdump counts the
+    1 KB per block that CUDA 12.9 reserves on sm_100 once any kernel of the module uses cp.async)."""
     out = subprocess.run(["cuobjdump", "-res-usage", lbm.LIB_PATH], capture_output=True, text=True).stdout
     m = re.search(r"Function _ZN5lbm3d6k_stepILi1ELi0ELb1ELb0EEEvNS_2KPE:\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", out)
     assert m, out[:500]
     reg, stack, shared, local = (int(x) for x in m.groups())
-    assert reg <= 102 and stack == 0 and shared == 0 and local == 0, (reg, stack, shared, local)
+    assert reg <= 102 and stack == 0 and shared in (0, 1024) and local == 0, (reg, stack, shared, local)
     # the D2Q9 kernel: 4 blocks of 256 threads per SM
     m = re.search(r"Function _ZN5lbm2d7k2_stepENS_3KP2E:\s*\n\s*REG:(\d+) STACK:(\d+)", out)
     assert m and int(m.group(1)) <= 64 and int(m.group(2)) == 0

@@ -24,6 +24,12 @@ def ngpus():
                                         (2, ["--halo", "p2p", "--N", "21", "--Re", "400", "--steps", "30", "--track", "0"]),
                                         (4, ["--halo", "p2p", "--N", "30", "--steps", "30", "--diag", "1"]),
                                         (8, ["--halo", "p2p", "--N", "40", "--steps", "24"]),
+                                        # two iterations per pass on slabs: two ghost planes per side, 19 planes per face
+                                        (2, ["--pair", "1", "--N", "32", "--steps", "41"]),
+                                        (2, ["--pair", "1", "--pair-variant", "1", "--pair-lz", "3", "--N", "21", "--Re", "400", "--steps", "30", "--track", "0"]),
+                                        (2, ["--pair", "1", "--pair-variant", "2", "--N", "16", "--method", "0", "--Re", "20", "--diag", "1", "--steps", "26"]),
+                                        (4, ["--pair", "1", "--N", "33", "--steps", "30"]), (8, ["--pair", "1", "--N", "40", "--steps", "25"]),
+                                        (2, ["--pair", "1", "--N", "256", "--Re", "1000", "--steps", "9"]),
                                         (2, ["--dim", "2", "--N", "24", "--M", "41", "--Re", "40", "--steps", "50"]),
                                         (4, ["--dim", "2", "--N", "100", "--M", "30", "--Re", "100", "--steps", "40"])])
 def test_slab_run_matches_oracle(world, args):

@@ -24,6 +24,9 @@ ap.add_argument("--dim", type=int, default=3)
 ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"])
 ap.add_argument("--track", type=int, default=1)
 ap.add_argument("--M", type=int, default=40)
+ap.add_argument("--pair", type=int, default=-1, help="two-iterations-per-pass kernel (k_step_pair): -1 library default, 0 off, 1 on")
+ap.add_argument("--pair-variant", type=int, default=-1)
+ap.add_argument("--pair-lz", type=int, default=0)
 a = ap.parse_args()
 rank, world, local = D.env_rank()
 dist = D.init_process_group()
@@ -70,6 +73,10 @@ sim = lbm.Cavity3D(rank=rank, nranks=world, device=local, nccl_id=nid, track_res
 sim.set_option("host_local_layout", 1)
 if a.halo == "p2p" and world > 1:
     D.connect_direct_halo(sim)
+if a.pair >= 0:
+    sim.set_option("pair", a.pair)
+    sim.set_option("pair_variant", a.pair_variant)
+    sim.set_option("pair_lz", a.pair_lz)
 info = sim.info()
 res = []
 for n in (1, 1, 1, a.steps - 3):
@@ -95,7 +102,7 @@ if rank == 0:
     rho_same = np.array_equal(rho.reshape(-1).view(np.uint64), o.macrovars()["rho"].view(np.uint64))
     res_ok = (not a.track) or all(abs(x - y) <= 1e-12 * abs(y) for x, y in zip(res, ores))
     ok = same and rho_same and res_ok
-    print(json.dumps({"world": world, "halo": a.halo, "N": a.N, "steps": a.steps, "bit_equal": bool(same), "rho_equal": bool(rho_same),
+    print(json.dumps({"world": world, "halo": a.halo, "pair": a.pair, "N": a.N, "steps": a.steps, "bit_equal": bool(same), "rho_equal": bool(rho_same),
                       "residual_ok": bool(res_ok), "residuals": res, "oracle_residuals": ores,
                       "sha256": hashlib.sha256(full.tobytes()).hexdigest()}), flush=True)
 dist.barrier()

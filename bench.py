@@ -161,7 +161,7 @@ def cpu_reference_2d(N, threads):
     exe = O.ref2d_binary(**cfg)
     if not os.path.exists(exe):
         return None
-    ranks = max(3, min(threads, N // 8))
+    ranks = max(3, min(threads, N // 8, 128))   # oracle/mpi_shim: SHIM_MAXP
     with tempfile.TemporaryDirectory() as tmp:
         t0 = time.perf_counter()
         r = subprocess.run([exe], capture_output=True, text=True, cwd=tmp, env=dict(os.environ, SHIM_NP=str(ranks)), check=True)

@@ -136,7 +136,7 @@ static int launch_pair_v(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, cudaStream_t
             CK(cudaFuncSetAttribute(lbm3d::k_step_pair<M_, G_, TY, MINB, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
             attr_done[c->dev & 15] = true;                                                                   \
         }                                                                                                    \
-        lbm3d::k_step_pair<M_, G_, TY, MINB, STAGE><<<grid, blk, smem, st>>>(p);                              \
+        lbm3d::k_step_pair<M_, G_, TY, MINB, STAGE><<<grid, blk, smem, st>>>(p, c->tmap[c->cur]);                              \
     } while (0)
     if (c->prm.METHOD == 1) {
         if (g1) LBM_PAIR_LAUNCH(1, true); else LBM_PAIR_LAUNCH(1, false);
@@ -150,12 +150,46 @@ static int launch_pair_v(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, cudaStream_t
 
 // Tile variants: rows per block, resident blocks per SM, staging mode (lbm3d_pair.cuh).
 struct PairVariant { int ty, minb, stage; };
-static const PairVariant PAIR_VARIANTS[] = {{20, 1, 0}, {16, 1, 2}, {10, 2, 0}, {16, 1, 0}, {16, 1, 1}, {17, 1, 1}, {12, 1, 1}, {10, 2, 3}};
+static const PairVariant PAIR_VARIANTS[] = {{20, 1, 0}, {16, 1, 2}, {10, 2, 0}, {16, 1, 0}, {16, 1, 1}, {17, 1, 1}, {12, 1, 1}, {10, 2, 3}, {16, 1, 4}, {8, 2, 4}, {12, 1, 4}};
 static const int PAIR_NVARIANTS = (int)(sizeof(PAIR_VARIANTS) / sizeof(PAIR_VARIANTS[0]));
 static const int PAIR_DEFAULT_VARIANT = 7;   // 2 blocks of 32 x 10 per SM, no prefetch: best of profiles/r02_pair_ab.md
 
 static int pair_variant(const lbm_ctx *c) {
-    return (c->pair_variant >= 0 && c->pair_variant < PAIR_NVARIANTS) ? c->pair_variant : PAIR_DEFAULT_VARIANT;
+    int v = (c->pair_variant >= 0 && c->pair_variant < PAIR_NVARIANTS) ? c->pair_variant : PAIR_DEFAULT_VARIANT;
+    if (PAIR_VARIANTS[v].stage == 4 && !c->tmap_ok) v = 7;   // TMA needs 16-byte strides (N even)
+    return v;
+}
+
+// One 4-D tensor map per lattice for the TMA-staged variants: dims (x, y, z incl. ghost planes, q),
+// box = one 32 x TY tile of one population plane.  The encoder lives in libcuda; it is fetched through
+// the runtime (cudaGetDriverEntryPoint), so the library needs no -lcuda.
+typedef CUresult (*lbm_tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                       const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_tensor_maps(lbm_ctx *c) {
+    c->tmap_ok = false;
+    if (c->N % 2) return LBM_OK;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+        q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return LBM_OK;   // no TMA variants; everything else works
+    }
+    const int ty = PAIR_VARIANTS[(c->pair_variant >= 0 && c->pair_variant < PAIR_NVARIANTS) ? c->pair_variant : PAIR_DEFAULT_VARIANT].ty;
+    for (int l = 0; l < 2; l++) {
+        const cuuint64_t dims[4] = {(cuuint64_t)c->N, (cuuint64_t)c->N, (cuuint64_t)(c->nzl + 2 * c->G), (cuuint64_t)lbm3d::Q};
+        const cuuint64_t strides[3] = {(cuuint64_t)c->N * 8, (cuuint64_t)c->N2 * 8, (cuuint64_t)c->PS * 8};
+        const cuuint32_t box[4] = {(cuuint32_t)lbm3d::PAIR_TX, (cuuint32_t)ty, 1, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = ((lbm_tmap_encode_fn)fn)(&c->tmap[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, c->lat[l], dims, strides, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return LBM_OK;
+    }
+    c->tmap_ok = true;
+    c->tmap_ty = ty;
+    return LBM_OK;
 }
 static int pair_ty(const lbm_ctx *c) { return PAIR_VARIANTS[pair_variant(c)].ty; }
 
@@ -168,7 +202,10 @@ static int launch_pair(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, cudaStream_t s
         case 4: return launch_pair_v<16, 1, 1>(c, p, grid, st);
         case 5: return launch_pair_v<17, 1, 1>(c, p, grid, st);
         case 6: return launch_pair_v<12, 1, 1>(c, p, grid, st);
-        default: return launch_pair_v<10, 2, 3>(c, p, grid, st);
+        case 7: return launch_pair_v<10, 2, 3>(c, p, grid, st);
+        case 8: return launch_pair_v<16, 1, 4>(c, p, grid, st);
+        case 9: return launch_pair_v<8, 2, 4>(c, p, grid, st);
+        default: return launch_pair_v<12, 1, 4>(c, p, grid, st);
     }
 }
 
@@ -189,6 +226,7 @@ static int run_pair(lbm_ctx *c) {
     kp_set_lattices(c, &p, c->lat[c->cur], c->lat[dsti]);
     p.side_rd = side_slot(c, t + 2);  p.side_wr = side_slot(c, t);
     p.side_rd2 = side_slot(c, t + 3); p.side_wr2 = side_slot(c, t + 1);
+    if (PAIR_VARIANTS[pair_variant(c)].stage == 4 && c->tmap_ty != pair_ty(c)) make_tensor_maps(c);
     const int ty = pair_ty(c);
     const unsigned gx = (c->N + lbm3d::PAIR_OX - 1) / lbm3d::PAIR_OX, gy = (c->N + ty - 3) / (ty - 2);
     int Lz = c->pair_lz > 0 ? c->pair_lz : 32;

@@ -27,6 +27,8 @@
 // the two fused iterations read {t+2, t+3} and write {t, t+1} (mod 4): redundant step-A work in
 // neighbouring blocks can neither race with step B nor see its output.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched with cudaGetDriverEntryPoint)
+
 #include "lbm3d_kernels.cuh"
 
 namespace lbm3d {
@@ -34,7 +36,9 @@ namespace lbm3d {
 constexpr int PAIR_TX = 32;       // threads per tile row (one warp)
 constexpr int PAIR_OX = 30;       // output cells per tile row
 
-__host__ __device__ constexpr int pair_smem_bytes(int TY, int STAGE) { return (32 + (STAGE == 1 ? 19 : 0)) * PAIR_TX * TY * (int)sizeof(double); }
+__host__ __device__ constexpr int pair_smem_bytes(int TY, int STAGE) {
+    return (32 + ((STAGE == 1 || STAGE == 4) ? 19 : 0)) * PAIR_TX * TY * (int)sizeof(double) + (STAGE == 4 ? 16 : 0);
+}
 
 #define LBM_PREFETCH_L2(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))
 
@@ -45,13 +49,17 @@ __host__ __device__ constexpr int pair_smem_bytes(int TY, int STAGE) { return (3
 //         1: the 19 pulls of plane pz+1 are issued as asynchronous copies (cp.async, LDGSTS) into a
 //            per-thread staging slot of shared memory right after the first barrier and land while
 //            step B computes, so step A never waits for HBM (costs 152 B of shared memory per cell);
+//         4: the same staging done by the TMA unit: ONE thread issues 19 tensor copies
+//            (cp.async.bulk.tensor.4d, one 32 x TY box per population, coordinates shifted by -c_q,
+//            out-of-range elements zero-filled) that complete on an mbarrier -- no per-thread address
+//            arithmetic, no load instructions, nothing in the LSU queue (needs N even: 16-byte strides);
 //         2: like 0 but software-pipelined through 19 extra registers (slower: 128 registers leave
 //            16 warps per SM and the pulls still stall -- kept for the record, profiles/r02_pair_ab.md).
 //
 // grid = (ceil(N/30), ceil(N/(TY-2)), ceil((zhi-zlo)/Lz)); block = (32, TY); dynamic smem = pair_smem_bytes(TY).
 template <int METHOD, bool G1, int TY, int MINB, int STAGE>
-__global__ void __launch_bounds__(PAIR_TX *TY, MINB) k_step_pair(const __grid_constant__ KP p) {
-    extern __shared__ double sm[];
+__global__ void __launch_bounds__(PAIR_TX *TY, MINB) k_step_pair(const __grid_constant__ KP p, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) double sm[];
     constexpr int NT = PAIR_TX * TY;
     double *const s_up = sm;             // [3 planes][4][NT]   populations 9, 11, 16, 18
     double *const s_in = sm + 12 * NT;   // [2 planes][8][NT]   populations 1, 2, 3, 4, 7, 8, 13, 14
@@ -87,6 +95,30 @@ __global__ void __launch_bounds__(PAIR_TX *TY, MINB) k_step_pair(const __grid_co
         _Pragma("unroll") for (int q_ = 0; q_ < Q; q_++)                                                            \
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_ + q_ * NT * 8), "l"(p.srcq[q_] + (at)) : "memory"); \
     }
+    // STAGE 4: TMA.  Box (32, TY, 1, 1) of population q at lattice coordinates (x - cx, y - cy, z - cz, q).
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(sm + (32 + 19) * NT);
+    const unsigned st_base = (unsigned)__cvta_generic_to_shared(s_st);
+    const bool tma_leader = (tx == 0 && ty == 0);
+    const int tile_x = (int)blockIdx.x * PAIR_OX - 1, tile_y = (int)blockIdx.y * (TY - 2) - 1;
+    unsigned tma_phase = 0;
+#define LBM_TMA_ONE(q, cx, cy, cz, wq)                                                                                     \
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" \
+                 ::"r"(st_base + (q) * NT * 8), "l"(&tmap), "r"(mbar), "r"(tile_x - (cx)), "r"(tile_y - (cy)), "r"(zc_ - (cz)), "r"(q) \
+                 : "memory");
+#define LBM_TMA_PLANE(zplane)                                                                                              \
+    {                                                                                                                      \
+        const int zc_ = (zplane) + p.G;                                                                                    \
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(19 * NT * 8) : "memory");   \
+        LBM_D3Q19_VEL(LBM_TMA_ONE)                                                                                         \
+    }
+    if (STAGE == 4) {
+        if (tma_leader) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the init must be visible to the TMA unit
+        }
+        __syncthreads();
+        if (tma_leader && LBM_PLANE_IN_BOX(z0 - 1)) LBM_TMA_PLANE(z0 - 1)
+    }
     double fn[Q];                              // PIPE: the pulls of the next plane, in flight
     if (PIPE) {
         if (in_box && LBM_PLANE_IN_BOX(z0 - 1)) LBM_PULL_INTO(fn, cell)
@@ -102,14 +134,21 @@ __global__ void __launch_bounds__(PAIR_TX *TY, MINB) k_step_pair(const __grid_co
         double f[Q];
         f[0] = 0.0; f[5] = 0.0; f[6] = 0.0;
         // ---- step A: S(t) from HBM -> S(t+1) into shared memory --------------------------------------
+        if (STAGE == 4 && (kg >= 0) && (kg <= p.Mz)) {   // the staged plane has landed (phase parity of the mbarrier)
+            asm volatile(
+                "{\n\t.reg .pred P1;\n\tLBM_TMA_WAIT:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+                "@P1 bra LBM_TMA_DONE;\n\tbra LBM_TMA_WAIT;\n\tLBM_TMA_DONE:\n\t}" ::"r"(mbar), "r"(tma_phase) : "memory");
+            tma_phase ^= 1;
+        }
         if (have_a) {
             if (PIPE) {
 #pragma unroll
                 for (int q = 0; q < Q; q++) f[q] = fn[q];
-            } else if (STAGE == 1) {
-                asm volatile("cp.async.wait_all;" ::: "memory");
+            } else if (STAGE == 1 || STAGE == 4) {
+                if (STAGE == 1) asm volatile("cp.async.wait_all;" ::: "memory");
 #pragma unroll
-                for (int q = 0; q < Q; q++) f[q] = s_st[q * NT + li];   // this thread's own copies: no barrier needed
+                for (int q = 0; q < Q; q++) f[q] = s_st[q * NT + li];   // STAGE 1: this thread's own copies, no barrier needed
             } else {
                 LBM_PULL_INTO(f, cell)
             }
@@ -145,9 +184,12 @@ __global__ void __launch_bounds__(PAIR_TX *TY, MINB) k_step_pair(const __grid_co
             if (in_box && pz < z1 && LBM_PLANE_IN_BOX(pz + 1)) LBM_STAGE_PLANE(cell + N2i)
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
+        if (STAGE == 4) {   // every thread has consumed the staged plane (barrier above): refill it
+            if (tma_leader && pz < z1 && LBM_PLANE_IN_BOX(pz + 1)) LBM_TMA_PLANE(pz + 1)
+        }
         // Warm L2 with the lines a later step A pulls (every (population, plane) pair is read exactly
         // once per block, so without this every pull is a DRAM-latency miss).
-        if (STAGE != 1 && STAGE != 3 && in_box && pz + (PIPE ? 1 : 0) < z1) {   // STAGE 3: variant 0 without the prefetch (A/B only)
+        if (STAGE != 1 && STAGE != 3 && STAGE != 4 && in_box && pz + (PIPE ? 1 : 0) < z1) {   // STAGE 3: variant 0 without the prefetch (A/B only)
             const int ahead = cell + (PIPE ? 2 : 1) * N2i;
 #define LBM_PF(q, cx, cy, cz, wq) LBM_PREFETCH_L2(p.srcq[q] + ahead);
             LBM_D3Q19_VEL(LBM_PF)
@@ -196,6 +238,8 @@ __global__ void __launch_bounds__(PAIR_TX *TY, MINB) k_step_pair(const __grid_co
     }
 #undef LBM_PULL_INTO
 #undef LBM_STAGE_PLANE
+#undef LBM_TMA_PLANE
+#undef LBM_TMA_ONE
 #undef LBM_PLANE_IN_BOX
 }
 

@@ -172,6 +172,7 @@ static int create3d(lbm_ctx *c) {
     CK(cudaGetLastError());
     c->cur = 0;
     c->steps = 0;
+    if ((rc = make_tensor_maps(c))) return rc;
     if (p.track_residual) {
         if ((rc = materialise_F(c))) return rc;  // Fbuf = w: the reference's f1 before iteration 0 (3D:96)
         if ((rc = ensure_partials(c))) return rc;
@@ -657,7 +658,7 @@ int lbm_set_option(lbm_ctx *c, const char *key, long long value) {
     } else if (!strcmp(key, "pair_variant")) {
         if (value < -1 || value >= PAIR_NVARIANTS) return fail(LBM_ERR_INVALID, "pair_variant must be in [-1, %d)", PAIR_NVARIANTS);
         c->pair_variant = (int)value;
-        return LBM_OK;
+        return make_tensor_maps(c);
     } else if (!strcmp(key, "pair_lz")) {
         if (value < 0) return fail(LBM_ERR_INVALID, "pair_lz must be >= 0");
         c->pair_lz = (int)value;

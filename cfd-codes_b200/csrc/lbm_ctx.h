@@ -129,6 +129,9 @@ struct lbm_ctx {
     cudaGraphExec_t graph_exec[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // two iterations per pass (k_step_pair): -1 auto, 0 off, 1 on; tile variant (PAIR_VARIANTS, -1 = default); planes per z segment
     int pair = -1, pair_variant = -1, pair_lz = 0;
+    CUtensorMap tmap[2];                  // TMA-staged variants: one 4-D map per lattice (x, y, z, q)
+    bool tmap_ok = false;
+    int tmap_ty = 0;                      // box rows the maps were encoded for
     // direct NVLink halo (lbm_peer_connect): neighbours' lattices / arrival flags mapped here
     bool p2p = false;
     long long p2p_base = 0;               // iteration count at which the direct halo was switched on

@@ -33,7 +33,7 @@ struct MPI_Request { int kind; void *buf; int count; int tag; };  /* kind 0 = nu
 #define MPI_SUM 1
 #define MPI_REQUEST_NULL (MPI_Request{0, nullptr, 0, 0})
 
-#define SHIM_MAXP 16
+#define SHIM_MAXP 128
 #define SHIM_TAGS 3
 #define SHIM_DEPTH 16
 #define SHIM_MAXCOUNT 16384

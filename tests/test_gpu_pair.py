@@ -48,6 +48,8 @@ def test_pair_kernel_matches_reference_hashes(lbm, tag, steps):
     (dict(N=61, Re=200), 1, 9), (dict(N=64, Re=253), 2, 0), (dict(N=96, Re=300), 5, 33),
     (dict(N=40, Re=30, METHOD=0), 1, 11), (dict(N=45, Re=100, GAMMA=2.0), 0, 6),
     (dict(N=35, Re=100), 6, 8), (dict(N=50, Re=100, DIAG=1), 7, 13), (dict(N=70, Re=200), 4, 0),
+    (dict(N=12, Re=100), 8, 0), (dict(N=34, Re=200, DIAG=1), 8, 5), (dict(N=64, Re=253), 9, 10), (dict(N=20, Re=20, METHOD=0, GAMMA=0.5), 10, 7),
+    (dict(N=96, Re=300), 8, 31), (dict(N=33, Re=100), 8, 6),   # odd N: the TMA variant falls back (needs 16-byte strides)
 ], ids=lambda v: "-".join("%s%s" % kv for kv in v.items()) if isinstance(v, dict) else str(v))
 def test_pair_kernel_tiles_and_segments_match_oracle(lbm, oracle, cfg, variant, lz):
     """Every kernel variant (tile rows, blocks per SM, register pipelining) and z-segment length, grids that are not multiples of the tile, tracked and

@@ -34,7 +34,7 @@ PEER_BLOB_BYTES = 320
 # every symbol include/lbm_b200.h declares
 ABI_SYMBOLS = [
     "lbm_default_params", "lbm_nccl_unique_id", "lbm_create", "lbm_peer_export", "lbm_peer_connect", "lbm_step", "lbm_step_timed", "lbm_timer_start",
-    "lbm_timer_stop", "lbm_residual",
+    "lbm_timer_stop", "lbm_residual", "lbm_converge",
     "lbm_get_f", "lbm_set_f", "lbm_set_f_async", "lbm_set_f_commit", "lbm_macrovars", "lbm_macrovars_async", "lbm_io_wait", "lbm_sync", "lbm_get_info", "lbm_set_option", "lbm_destroy",
     "lbm_last_error", "lbm_version",
 ]
@@ -58,6 +58,13 @@ class LbmInfo(C.Structure):
         ("device_bytes", C.c_longlong), ("plain_step_ms", C.c_double), ("plain_step_iterations", C.c_longlong),
         ("pair_enabled", C.c_int),
     ]
+
+
+class LbmBlockRecord(C.Structure):
+    _fields_ = [("iteration", C.c_longlong), ("df", C.c_double), ("status", C.c_int), ("last", C.c_int)]
+
+
+BLOCK_FN = C.CFUNCTYPE(None, C.POINTER(LbmBlockRecord), C.c_void_p)
 
 
 class LbmError(RuntimeError):
@@ -95,6 +102,8 @@ def load_library(path=None):
     L.lbm_timer_start.argtypes = [vp]
     L.lbm_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.lbm_residual.argtypes = [vp, C.POINTER(C.c_double)]
+    L.lbm_converge.argtypes = [vp, C.c_longlong, C.c_double, C.c_longlong, C.c_double, BLOCK_FN, C.c_void_p,
+                               C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
     L.lbm_get_f.argtypes = [vp, dp]
     L.lbm_set_f.argtypes = [vp, dp, dp]
     L.lbm_macrovars.argtypes = [vp, dp, dp, dp, dp, dp]
@@ -109,7 +118,7 @@ def load_library(path=None):
     L.lbm_last_error.restype = C.c_char_p
     L.lbm_version.restype = C.c_char_p
     for name in ("lbm_nccl_unique_id", "lbm_create", "lbm_peer_export", "lbm_peer_connect", "lbm_step", "lbm_step_timed", "lbm_timer_start", "lbm_timer_stop",
-                 "lbm_residual", "lbm_get_f", "lbm_set_f_async", "lbm_set_f_commit", "lbm_macrovars_async", "lbm_io_wait",
+                 "lbm_residual", "lbm_converge", "lbm_get_f", "lbm_set_f_async", "lbm_set_f_commit", "lbm_macrovars_async", "lbm_io_wait",
                  "lbm_set_f", "lbm_macrovars", "lbm_sync", "lbm_get_info", "lbm_set_option", "lbm_destroy"):
         getattr(L, name).restype = C.c_int
     if path == LIB_PATH:
@@ -200,6 +209,24 @@ class Cavity3D:
         _check(self._L.lbm_residual(self._h, C.byref(out)))
         return out.value
 
+    def converge(self, skip, thresh, max_blocks, df0, on_block=None):
+        """The reference's convergence loop (3D:103-124) as ONE call: up to max_blocks blocks of `skip`
+        iterations, df = diff * df0 after each, stop when df < thresh.  On one GPU the loop runs on
+        the device (conditional CUDA graph) without host synchronisation between the blocks.
+        Returns (blocks_done, last df, [(iteration, df), ...])."""
+        recs = []
+
+        def cb(rec, _user):
+            r = rec.contents
+            recs.append((r.iteration, r.df))
+            if on_block:
+                on_block(r.iteration, r.df)
+
+        fn = BLOCK_FN(cb)
+        done, df = C.c_longlong(), C.c_double()
+        _check(self._L.lbm_converge(self._h, skip, thresh, max_blocks, df0, fn, None, C.byref(done), C.byref(df)))
+        return done.value, df.value, recs
+
     def sync(self):
         _check(self._L.lbm_sync(self._h))
 
@@ -270,12 +297,11 @@ class Cavity3D:
         with open(path, "w") as fh:
             fh.write('TITLE="%s" VARIABLES="x", "y", "z", "u", "v", "w", "vmag" ZONE T="%s" I=%d J=%d K=%d F=POINT\n'
                      % (name, name, N, N, N))
-            for i in range(N):
-                for j in range(N):
-                    rows = ["%.10f, %.10f, %.10f, %.10f, %.10f, %.10f, %.10f\n"
-                            % (float(i), float(j), float(k), u[k, j, i], v[k, j, i], w[k, j, i], m[k, j, i])
-                            for k in range(N)]
-                    fh.write("".join(rows))
+            kk, jj = np.meshgrid(np.arange(N, dtype=np.float64), np.arange(N, dtype=np.float64))   # rows: j outer, k inner
+            for i in range(N):     # one i-slab (N^2 lines) per formatting call
+                slab = np.column_stack([np.full(N * N, float(i)), jj.ravel(), kk.ravel(), u[:, :, i].T.ravel(),
+                                        v[:, :, i].T.ravel(), w[:, :, i].T.ravel(), m[:, :, i].T.ravel()])
+                np.savetxt(fh, slab, fmt="%.10f", delimiter=", ")
         return path
 
     def close(self):
@@ -298,23 +324,17 @@ class Cavity3D:
 
 def run_to_convergence(sim, THRESH=1e-12, skip=500, MAXITER=int(1e8), log=None):
     """The reference's driver loop (3D:93-124): iteration 0 normalises (df0 = 1/diff), then every
-    `skip` iterations df = diff*df0 and the loop stops when df < THRESH.  Returns (iterations, df)."""
+    `skip` iterations df = diff*df0 and the loop stops when df < THRESH.  Returns (iterations, df).
+    The blocks run inside Cavity3D.converge (device-side loop on one GPU)."""
     sim.step(1)
     df0 = sim.residual()
     if log:
         log("\nIteration 0:\ndf:\t%.3e" % df0)
     df0 = 1.0 / df0
-    t = 0
-    df = None
-    while t + skip < MAXITER:
-        sim.step(skip)
-        t += skip
-        df = sim.residual() * df0
-        if log:
-            log("\nIteration %d:\ndf/df0:\t%.3e" % (t, df))
-        if df < THRESH:
-            break
-    return t, df
+    blocks = max(0, (MAXITER - 1) // skip)
+    done, df, _ = sim.converge(skip, THRESH, blocks, df0,
+                               (lambda t, d: log("\nIteration %d:\ndf/df0:\t%.3e" % (t, d))) if log else None)
+    return done * skip, (df if done else None)
 
 
 class Cavity2D:
@@ -377,8 +397,8 @@ class Cavity2D:
     def macro(self, out=None):
         n = self.N * self.M
         if out is None:
-            out = {k: np.zeros(n, dtype=np.float64) for k in ("u", "v", "rho")}
-        _check(self._L.lbm_macrovars(self._h, _ptr(out["u"]), _ptr(out["v"]), None, _ptr(out["rho"]), None))
+            out = {k: np.zeros(n, dtype=np.float64) for k in ("u", "v", "rho", "vmag")}
+        _check(self._L.lbm_macrovars(self._h, _ptr(out["u"]), _ptr(out["v"]), None, _ptr(out["rho"]), _ptr(out.get("vmag"))))
         return out
 
     def info(self):

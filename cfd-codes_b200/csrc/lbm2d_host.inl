@@ -183,23 +183,22 @@ static int copy_dist2d(lbm_ctx *c, double *host, bool to_host) {
 
 static int macrovars2d(lbm_ctx *c, double *u, double *v, double *rho, double *vmag) {
     int rc;
-    for (int a = 0; a < 3; a++)
-        if (!c->out2[a]) { if ((rc = dev_alloc(c, &c->out2[a], c->FS))) return rc; }
+    for (int a = 0; a < 4; a++)
+        if (!c->out2[a] && (a < 3 || vmag)) { if ((rc = dev_alloc(c, &c->out2[a], c->FS))) return rc; }
     const int bx = block2d(c);
     const unsigned gx = (unsigned)((c->N + bx - 1) / bx);
     lbm2d::KP2 p = make_kp2(c, c->lat[c->cur], nullptr);
     p.u = c->out2[0]; p.v = c->out2[1]; p.rho = c->out2[2];
+    p.vmag = vmag ? c->out2[3] : nullptr;
     lbm2d::k2_macro<false><<<dim3(gx, c->nyl), bx, 0, c->s_main>>>(p);
     c->launches++;
     CK(cudaGetLastError());
     const long long off = c->host_local ? 0 : (long long)c->j0 * c->N;
-    double *host[3] = {u, v, rho};
-    for (int a = 0; a < 3; a++)
+    double *host[4] = {u, v, rho, vmag};
+    for (int a = 0; a < 4; a++)
         if (host[a])
             CK(cudaMemcpyAsync(host[a] + off, c->out2[a], (size_t)c->FS * 8, cudaMemcpyDeviceToHost, c->s_main));
     CK(cudaStreamSynchronize(c->s_main));
-    if (vmag && u && v)
-        for (long long n = 0; n < c->FS; n++) vmag[off + n] = sqrt(u[off + n] * u[off + n] + v[off + n] * v[off + n]);
     return LBM_OK;
 }
 

@@ -27,6 +27,7 @@ struct KP2 {
     const double *own[9];   // un-shifted:  own[k][cell]  = dist_old[k](i, j)             (wall bounce 2D:308-356)
     double *dstq[9];
     double *u, *v, *rho;    // macroVars state [rows][N] (2D:132-136)
+    double *vmag;           // output path only: sqrt(u^2 + v^2), may be null
     double *partials;
     int N, M;               // width, global height
     int nyl, j0;            // owned rows, global index of local row 0
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(256) k2_macro(const __grid_constant__ KP2 p) {
         p.u[o] = nu;
         p.rho[o] = nr;
         p.v[o] = nv;
+        if (!DIFF && p.vmag) p.vmag[o] = sqrt(nu * nu + nv * nv);   // output path only
     }
     if (!DIFF) return;
 #pragma unroll

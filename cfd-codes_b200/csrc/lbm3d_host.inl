@@ -124,8 +124,9 @@ static void launch_step(lbm_ctx *c, int mode, const lbm3d::KP &p, dim3 grid, dim
 static int halo_exchange(lbm_ctx *c, double *L, cudaStream_t st, bool deep, long long next_t);
 
 // ---- two iterations per pass (lbm3d_pair.cuh) -------------------------------------------------------
+// `prepare` only raises the kernel's dynamic shared memory limit (done outside stream capture).
 template <int TY, int MINB, int STAGE>
-static int launch_pair_v(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, cudaStream_t st) {
+static int launch_pair_v(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, cudaStream_t st, bool prepare) {
     const bool g1 = (c->prm.GAMMA == 1.0);
     const dim3 blk(lbm3d::PAIR_TX, TY, 1);
     const int smem = lbm3d::pair_smem_bytes(TY, STAGE);
@@ -136,6 +137,7 @@ static int launch_pair_v(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, cudaStream_t
             CK(cudaFuncSetAttribute(lbm3d::k_step_pair<M_, G_, TY, MINB, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
             attr_done[c->dev & 15] = true;                                                                   \
         }                                                                                                    \
+        if (prepare) return LBM_OK;                                                                          \
         lbm3d::k_step_pair<M_, G_, TY, MINB, STAGE><<<grid, blk, smem, st>>>(p, c->tmap[c->cur]);                              \
     } while (0)
     if (c->prm.METHOD == 1) {
@@ -180,7 +182,7 @@ static int make_tensor_maps(lbm_ctx *c) {
     for (int l = 0; l < 2; l++) {
         const cuuint64_t dims[4] = {(cuuint64_t)c->N, (cuuint64_t)c->N, (cuuint64_t)(c->nzl + 2 * c->G), (cuuint64_t)lbm3d::Q};
         const cuuint64_t strides[3] = {(cuuint64_t)c->N * 8, (cuuint64_t)c->N2 * 8, (cuuint64_t)c->PS * 8};
-        const cuuint32_t box[4] = {(cuuint32_t)lbm3d::PAIR_TX, (cuuint32_t)ty, 1, 1};
+        const cuuint32_t box[4] = {(cuuint32_t)lbm3d::PAIR_BOX_X, (cuuint32_t)ty, 1, 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = ((lbm_tmap_encode_fn)fn)(&c->tmap[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, c->lat[l], dims, strides, box, estr,
                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -193,19 +195,19 @@ static int make_tensor_maps(lbm_ctx *c) {
 }
 static int pair_ty(const lbm_ctx *c) { return PAIR_VARIANTS[pair_variant(c)].ty; }
 
-static int launch_pair(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, cudaStream_t st) {
+static int launch_pair(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, cudaStream_t st, bool prepare = false) {
     switch (pair_variant(c)) {
-        case 0: return launch_pair_v<20, 1, 0>(c, p, grid, st);
-        case 1: return launch_pair_v<16, 1, 2>(c, p, grid, st);
-        case 2: return launch_pair_v<10, 2, 0>(c, p, grid, st);
-        case 3: return launch_pair_v<16, 1, 0>(c, p, grid, st);
-        case 4: return launch_pair_v<16, 1, 1>(c, p, grid, st);
-        case 5: return launch_pair_v<17, 1, 1>(c, p, grid, st);
-        case 6: return launch_pair_v<12, 1, 1>(c, p, grid, st);
-        case 7: return launch_pair_v<10, 2, 3>(c, p, grid, st);
-        case 8: return launch_pair_v<16, 1, 4>(c, p, grid, st);
-        case 9: return launch_pair_v<8, 2, 4>(c, p, grid, st);
-        default: return launch_pair_v<12, 1, 4>(c, p, grid, st);
+        case 0: return launch_pair_v<20, 1, 0>(c, p, grid, st, prepare);
+        case 1: return launch_pair_v<16, 1, 2>(c, p, grid, st, prepare);
+        case 2: return launch_pair_v<10, 2, 0>(c, p, grid, st, prepare);
+        case 3: return launch_pair_v<16, 1, 0>(c, p, grid, st, prepare);
+        case 4: return launch_pair_v<16, 1, 1>(c, p, grid, st, prepare);
+        case 5: return launch_pair_v<17, 1, 1>(c, p, grid, st, prepare);
+        case 6: return launch_pair_v<12, 1, 1>(c, p, grid, st, prepare);
+        case 7: return launch_pair_v<10, 2, 3>(c, p, grid, st, prepare);
+        case 8: return launch_pair_v<16, 1, 4>(c, p, grid, st, prepare);
+        case 9: return launch_pair_v<8, 2, 4>(c, p, grid, st, prepare);
+        default: return launch_pair_v<12, 1, 4>(c, p, grid, st, prepare);
     }
 }
 
@@ -302,6 +304,7 @@ static int ensure_partials(lbm_ctx *c) {
 // -- and the x = N-1 stale-f14 row of the slot that kernel reads.
 static const int Q_IN[9] = {0, 1, 2, 3, 4, 7, 8, 13, 14};   // cz = 0
 static int halo_exchange(lbm_ctx *c, double *L, cudaStream_t st, bool deep, long long next_t) {
+    if (c->slab_emulation) return LBM_OK;
     const int r = c->prm.rank, P = c->prm.nranks, G = c->G;
     const size_t n = (size_t)c->N2;
     const long long PS = c->PS, N2 = c->N2, nzl = c->nzl;

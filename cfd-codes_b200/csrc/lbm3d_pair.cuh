@@ -36,8 +36,12 @@ namespace lbm3d {
 constexpr int PAIR_TX = 32;       // threads per tile row (one warp)
 constexpr int PAIR_OX = 30;       // output cells per tile row
 
+constexpr int PAIR_BOX_X = 34;    // TMA box width: the tile's 32 columns + one on either side
+// doubles per population in the TMA staging area (box rows are dense; every box 128-byte aligned)
+__host__ __device__ constexpr int pair_tma_block(int TY) { return ((TY * PAIR_BOX_X * 8 + 127) / 128) * 16; }
 __host__ __device__ constexpr int pair_smem_bytes(int TY, int STAGE) {
-    return (32 + ((STAGE == 1 || STAGE == 4) ? 19 : 0)) * PAIR_TX * TY * (int)sizeof(double) + (STAGE == 4 ? 16 : 0);
+    return 32 * PAIR_TX * TY * (int)sizeof(double) +
+           (STAGE == 1 ? 19 * PAIR_TX * TY * (int)sizeof(double) : 0) + (STAGE == 4 ? 19 * pair_tma_block(TY) * (int)sizeof(double) + 16 : 0);
 }
 
 #define LBM_PREFETCH_L2(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))
@@ -50,9 +54,12 @@ __host__ __device__ constexpr int pair_smem_bytes(int TY, int STAGE) {
 //            per-thread staging slot of shared memory right after the first barrier and land while
 //            step B computes, so step A never waits for HBM (costs 152 B of shared memory per cell);
 //         4: the same staging done by the TMA unit: ONE thread issues 19 tensor copies
-//            (cp.async.bulk.tensor.4d, one 32 x TY box per population, coordinates shifted by -c_q,
-//            out-of-range elements zero-filled) that complete on an mbarrier -- no per-thread address
-//            arithmetic, no load instructions, nothing in the LSU queue (needs N even: 16-byte strides);
+//            (cp.async.bulk.tensor.4d, one 34 x TY box per population, rows and plane shifted by
+//            -(cy, cz), out-of-range elements zero-filled) that complete on an mbarrier -- no
+//            per-thread address arithmetic, no load instructions, nothing in the LSU queue.  A box must
+//            start on a 16-byte boundary (measured: tools/tma_probe.cu), so every box starts at the
+//            even column 30*bx - 2 and is two columns wider than the tile; the x shift -cx is applied
+//            when the thread reads its value back.  Needs N even (16-byte row stride);
 //         2: like 0 but software-pipelined through 19 extra registers (slower: 128 registers leave
 //            16 warps per SM and the pulls still stall -- kept for the record, profiles/r02_pair_ab.md).
 //
@@ -64,7 +71,8 @@ __global__ void __launch_bounds__(PAIR_TX *TY, MINB) k_step_pair(const __grid_co
     double *const s_up = sm;             // [3 planes][4][NT]   populations 9, 11, 16, 18
     double *const s_in = sm + 12 * NT;   // [2 planes][8][NT]   populations 1, 2, 3, 4, 7, 8, 13, 14
     double *const s_dn = sm + 28 * NT;   // [4][NT]             populations 10, 12, 15, 17
-    double *const s_st = sm + 32 * NT;   // [19][NT]            STAGE 1: this thread's pulls of the next plane
+    double *const s_st = sm + 32 * NT;   // STAGE 1: [19][NT] this thread's pulls of the next plane; STAGE 4: [19][TY][34] TMA boxes
+    constexpr int SB = pair_tma_block(TY);
     constexpr bool PIPE = (STAGE == 2);
 
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -95,20 +103,20 @@ __global__ void __launch_bounds__(PAIR_TX *TY, MINB) k_step_pair(const __grid_co
         _Pragma("unroll") for (int q_ = 0; q_ < Q; q_++)                                                            \
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_ + q_ * NT * 8), "l"(p.srcq[q_] + (at)) : "memory"); \
     }
-    // STAGE 4: TMA.  Box (32, TY, 1, 1) of population q at lattice coordinates (x - cx, y - cy, z - cz, q).
-    const unsigned mbar = (unsigned)__cvta_generic_to_shared(sm + (32 + 19) * NT);
+    // STAGE 4: TMA.  Box (34, TY, 1, 1) of population q at lattice coordinates (30*bx - 2, y - cy, z - cz, q).
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(sm + 32 * NT + 19 * SB);
     const unsigned st_base = (unsigned)__cvta_generic_to_shared(s_st);
     const bool tma_leader = (tx == 0 && ty == 0);
     const int tile_x = (int)blockIdx.x * PAIR_OX - 1, tile_y = (int)blockIdx.y * (TY - 2) - 1;
     unsigned tma_phase = 0;
 #define LBM_TMA_ONE(q, cx, cy, cz, wq)                                                                                     \
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" \
-                 ::"r"(st_base + (q) * NT * 8), "l"(&tmap), "r"(mbar), "r"(tile_x - (cx)), "r"(tile_y - (cy)), "r"(zc_ - (cz)), "r"(q) \
+                 ::"r"(st_base + (q) * SB * 8), "l"(&tmap), "r"(mbar), "r"(tile_x - 1), "r"(tile_y - (cy)), "r"(zc_ - (cz)), "r"(q) \
                  : "memory");
 #define LBM_TMA_PLANE(zplane)                                                                                              \
     {                                                                                                                      \
         const int zc_ = (zplane) + p.G;                                                                                    \
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(19 * NT * 8) : "memory");   \
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(19 * TY * PAIR_BOX_X * 8) : "memory"); \
         LBM_D3Q19_VEL(LBM_TMA_ONE)                                                                                         \
     }
     if (STAGE == 4) {
@@ -145,10 +153,15 @@ __global__ void __launch_bounds__(PAIR_TX *TY, MINB) k_step_pair(const __grid_co
             if (PIPE) {
 #pragma unroll
                 for (int q = 0; q < Q; q++) f[q] = fn[q];
-            } else if (STAGE == 1 || STAGE == 4) {
-                if (STAGE == 1) asm volatile("cp.async.wait_all;" ::: "memory");
+            } else if (STAGE == 4) {
+                const double *b = s_st + ty * PAIR_BOX_X + tx + 1;     // column tx of the tile = column tx+1 of the box
+#define LBM_UNBOX(q, cx, cy, cz, wq) f[q] = b[(q) * SB - (cx)];
+                LBM_D3Q19_VEL(LBM_UNBOX)
+#undef LBM_UNBOX
+            } else if (STAGE == 1) {
+                asm volatile("cp.async.wait_all;" ::: "memory");
 #pragma unroll
-                for (int q = 0; q < Q; q++) f[q] = s_st[q * NT + li];   // STAGE 1: this thread's own copies, no barrier needed
+                for (int q = 0; q < Q; q++) f[q] = s_st[q * NT + li];   // this thread's own copies, no barrier needed
             } else {
                 LBM_PULL_INTO(f, cell)
             }

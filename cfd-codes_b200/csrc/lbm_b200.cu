@@ -23,6 +23,7 @@
 #include "lbm_ctx.h"
 #include "lbm3d_host.inl"
 #include "lbm2d_host.inl"
+#include "lbm3d_converge.inl"
 
 // ---- C ABI ---------------------------------------------------------------------------------------
 extern "C" {
@@ -88,7 +89,7 @@ int lbm_destroy(lbm_ctx *c) {
     if (c->ev_commit) cudaEventDestroy(c->ev_commit);
     if (c->s_copy) { cudaStreamSynchronize(c->s_copy); cudaStreamDestroy(c->s_copy); }
     cudaFree(c->u2); cudaFree(c->v2); cudaFree(c->rho2);
-    for (int a = 0; a < 3; a++) cudaFree(c->out2[a]);
+    for (int a = 0; a < 4; a++) cudaFree(c->out2[a]);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
@@ -97,6 +98,9 @@ int lbm_destroy(lbm_ctx *c) {
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     drop_graphs(c);
+    drop_converge_graph(c);
+    cudaFree(c->conv_params);
+    if (c->conv_log) cudaFreeHost(c->conv_log);
     for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->s_halo) cudaStreamDestroy(c->s_halo);
@@ -239,15 +243,23 @@ int lbm_create(const lbm_params *p, lbm_ctx **out) {
         CKD(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
         CKD(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
         CKD(cudaEventCreateWithFlags(&c->ev_int, cudaEventDisableTiming));
-        if ((rc = nccl_load())) { lbm_destroy(c); return rc; }
-        ncclUniqueId id;
-        memcpy(&id, p->nccl_id, LBM_NCCL_ID_BYTES);
-        ncclResult_t r = g_nccl.CommInitRank(&c->comm, p->nranks, id, p->rank);
-        if (r != ncclSuccess) {
-            rc = fail(LBM_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
-            c->comm = nullptr;
-            lbm_destroy(c);
-            return rc;
+        // Profiling aid (tools/README.md): LBM_B200_SLAB_EMULATION=1 runs ONE rank of a multi-GPU
+        // decomposition without its neighbours -- same slab, same launches, exchanges skipped (the ghost
+        // planes keep their initial values, so the RESULTS ARE NOT THE CAVITY'S) -- so that ncu, which must
+        // not wrap a multi-rank command, can capture the slab kernels on a single GPU.
+        const char *emu = getenv("LBM_B200_SLAB_EMULATION");
+        c->slab_emulation = emu && emu[0] == '1';
+        if (!c->slab_emulation) {
+            if ((rc = nccl_load())) { lbm_destroy(c); return rc; }
+            ncclUniqueId id;
+            memcpy(&id, p->nccl_id, LBM_NCCL_ID_BYTES);
+            ncclResult_t r = g_nccl.CommInitRank(&c->comm, p->nranks, id, p->rank);
+            if (r != ncclSuccess) {
+                rc = fail(LBM_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+                c->comm = nullptr;
+                lbm_destroy(c);
+                return rc;
+            }
         }
     }
 #undef CKD
@@ -379,6 +391,67 @@ int lbm_step(lbm_ctx *c, long long n) {
     return LBM_OK;
 }
 
+int lbm_converge(lbm_ctx *c, long long skip, double thresh, long long max_blocks, double df0, lbm_block_fn on_block,
+                 void *user, long long *blocks_done, double *df_last) {
+    if (!c) return fail(LBM_ERR_INVALID, "null context");
+    if (skip < 1 || max_blocks < 0) return fail(LBM_ERR_INVALID, "lbm_converge: bad skip / max_blocks");
+    if (blocks_done) *blocks_done = 0;
+    if (df_last) *df_last = 0.0;
+    if (max_blocks == 0) return LBM_OK;
+    if (c->unstable) return fail(LBM_ERR_UNSTABLE, "Error: negative feq.  Therefore, unstable.");
+    CK(cudaSetDevice(c->dev));
+    if (!converge_on_device(c, skip)) return converge_host_loop(c, skip, thresh, max_blocks, df0, on_block, user, blocks_done, df_last);
+
+    int rc;
+    if ((rc = ensure_Fbuf(c))) return rc;
+    if ((rc = ensure_partials(c))) return rc;
+    const int phase = (int)(c->steps % SIDE_DEPTH) * 2 + c->cur;
+    if (!c->conv_exec || c->conv_skip != skip || c->conv_phase != phase) {
+        if ((rc = build_converge_graph(c, skip))) return rc;
+    }
+    ConvParams hp;
+    hp.df0 = df0; hp.thresh = thresh; hp.skip = skip; hp.max_blocks = max_blocks;
+    hp.t_first = c->steps - 1;   // the first block's check is iteration (steps - 1) + skip
+    hp.blocks = 0;
+    c->conv_log->seq = 0;
+    CK(cudaMemcpyAsync(c->conv_params, &hp, sizeof hp, cudaMemcpyHostToDevice, c->s_main));
+    CK(cudaGraphLaunch(c->conv_exec, c->s_main));
+    // Report the blocks as their records arrive in mapped host memory: plain loads, no CUDA call.
+    long long seen = 0;
+    double df = 0.0;
+    int status = LBM_OK;
+    bool done = false;
+    unsigned spins = 0;
+    while (!done) {
+        const long long seq = c->conv_log->seq;
+        if (seq == seen) {
+            if ((++spins & 0xfff) == 0 && cudaStreamQuery(c->s_main) != cudaErrorNotReady) {
+                // the graph ended (or failed) without publishing a final record: leave through the sync below
+                if (c->conv_log->seq == seen) break;
+            }
+            continue;
+        }
+        __sync_synchronize();
+        for (; seen < seq; seen++) {
+            const lbm_block_record r = c->conv_log->rec[seen % CONV_RING];
+            df = r.df;
+            status = r.status;
+            if (on_block) on_block(&r, user);
+            if (r.last) done = true;
+        }
+    }
+    cudaGetLastError();
+    CK(cudaStreamSynchronize(c->s_main));   // the loop has ended: one synchronisation, after convergence
+    c->steps += seen * skip;
+    c->launches += seen * c->launches_per_block;
+    c->f_valid = true;           // the last iteration of a block stores the reference's f2
+    c->residual_ready = true;
+    if (blocks_done) *blocks_done = seen;
+    if (df_last) *df_last = df;
+    if (status == LBM_ERR_UNSTABLE) { c->unstable = true; return fail(LBM_ERR_UNSTABLE, "Error: negative feq.  Therefore, unstable."); }
+    return poll_flag(c);
+}
+
 int lbm_timer_start(lbm_ctx *c) {
     if (!c) return fail(LBM_ERR_INVALID, "null context");
     CK(cudaSetDevice(c->dev));
@@ -412,7 +485,7 @@ int lbm_residual(lbm_ctx *c, double *out) {
     if (!c->residual_ready) return fail(LBM_ERR_INVALID, "lbm_residual: no iteration since creation / lbm_set_f");
     CK(cudaSetDevice(c->dev));
     const double *src = c->d_red;
-    if (c->prm.nranks > 1) {
+    if (c->prm.nranks > 1 && !c->slab_emulation) {
         NK(g_nccl.AllReduce(c->d_red, c->d_red + 1, 1, ncclDouble, ncclSum, c->comm, c->s_main));
         src = c->d_red + 1;
     }
@@ -617,6 +690,7 @@ int lbm_get_info(lbm_ctx *c, lbm_info *o) {
 int lbm_set_option(lbm_ctx *c, const char *key, long long value) {
     if (!c || !key) return fail(LBM_ERR_INVALID, "null argument");
     drop_graphs(c);  // captured launches bake in the block shape and kernel variant
+    drop_converge_graph(c);
     if (!strcmp(key, "graphs")) {
         c->graphs = value < 0 ? -1 : (value != 0);
         return LBM_OK;
@@ -666,6 +740,9 @@ int lbm_set_option(lbm_ctx *c, const char *key, long long value) {
     } else if (!strcmp(key, "halo_timeout_ms")) {
         if (value < 1) return fail(LBM_ERR_INVALID, "halo_timeout_ms must be >= 1");
         c->halo_timeout_ms = value;
+        return LBM_OK;
+    } else if (!strcmp(key, "converge_on_device")) {
+        c->conv_mode = value != 0;
         return LBM_OK;
     } else if (!strcmp(key, "vec2")) {
         c->vec2 = value != 0;

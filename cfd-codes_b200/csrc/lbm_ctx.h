@@ -108,7 +108,7 @@ struct lbm_ctx {
     // dim = 2 (D2Q9): N x M, row slabs [j0, j1); lat[] = [9][nyl+2][N]; macroVars state u2/v2/rho2
     int M2 = 0, nyl = 0, j0 = 0, j1 = 0;
     double *u2 = nullptr, *v2 = nullptr, *rho2 = nullptr;
-    double *out2[3] = {nullptr, nullptr, nullptr};
+    double *out2[4] = {nullptr, nullptr, nullptr, nullptr};   // output staging: u, v, rho, vmag
     double lid6 = 0.0;
 
     long long steps = 0, launches = 0, bytes = 0;
@@ -132,6 +132,13 @@ struct lbm_ctx {
     CUtensorMap tmap[2];                  // TMA-staged variants: one 4-D map per lattice (x, y, z, q)
     bool tmap_ok = false;
     int tmap_ty = 0;                      // box rows the maps were encoded for
+    // device-side convergence loop (lbm3d_converge.inl): one conditional-WHILE graph, its parameters, the mapped host log
+    cudaGraph_t conv_graph = nullptr;
+    cudaGraphExec_t conv_exec = nullptr;
+    long long conv_skip = 0, launches_per_block = 0;
+    int conv_phase = -1, conv_mode = 1;
+    struct ConvParams *conv_params = nullptr;
+    struct ConvLog *conv_log = nullptr, *conv_log_dev = nullptr;
     // direct NVLink halo (lbm_peer_connect): neighbours' lattices / arrival flags mapped here
     bool p2p = false;
     long long p2p_base = 0;               // iteration count at which the direct halo was switched on
@@ -145,6 +152,7 @@ struct lbm_ctx {
     long long halo_timeout_ms = 600000;   // direct halo: wall-clock limit of one wait for a neighbour (option halo_timeout_ms)
     bool host_local = false;  // host arrays are compact local slabs instead of full LU4/LU3 arrays
     ncclComm_t comm = nullptr;
+    bool slab_emulation = false;   // LBM_B200_SLAB_EMULATION=1: one rank of a decomposition alone, no exchanges (ncu aid)
 };
 
 template <typename T>

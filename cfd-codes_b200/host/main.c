@@ -60,6 +60,29 @@ typedef struct {
     int status;
 } worker;
 
+typedef struct {
+    int root;
+    long long skip;
+    double cells, start;
+} block_printer;
+
+static double now(void);
+
+/* The reference's printf block after every residual check, 3D:113-117.  Called by lbm_converge on the
+ * worker's own thread as each block finishes on the GPU. */
+static void print_block(const lbm_block_record *r, void *user) {
+    block_printer *bp = (block_printer *)user;
+    const double stop = now() - bp->start;
+    if (bp->root) {
+        printf("\nIteration %lld:\n", r->iteration);
+        printf("df/df0:\t%.3e\n", r->df);
+        printf("Time:\t%.3e s\n", stop);
+        printf("LUPS:\t%.3e s\n", bp->cells * (double)bp->skip / stop);
+        fflush(stdout);
+    }
+    bp->start = now();
+}
+
 static double now(void) {
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -189,46 +212,44 @@ static void *run(void *arg) {
     }
     df0 = 1.0 / df0;
 
-    /* Rest of iterations, 3D:103-124: iteration t is checked when t % skip == 0.  `fields_taken`:
-     * the output fields were already read one iteration before the last (MAXITER exit, see header). */
-    double start = now();
+    /* Rest of iterations, 3D:103-124: iteration t is checked when t % skip == 0.  All blocks that end
+     * strictly before the last iteration run inside lbm_converge -- on one GPU a single device-side
+     * while loop, no host synchronisation between the blocks.  The block that contains the last
+     * iteration (MAXITER exit, see header) is stepped by hand.  `fields_taken`: the output fields were
+     * already read one iteration before the last. */
     const double cells = (double)o->N * (double)o->N * (double)o->N;
+    block_printer bp = {root, o->skip, cells, now()};
     long long t = 1;
     const long long last = (long long)o->MAXITER - 1;
-    int fields_taken = 0;
-    while (t <= last) {
+    int fields_taken = 0, converged = 0;
+    {
+        const long long whole = last >= 1 ? (last - 1) / o->skip : 0; /* checks at skip, 2*skip, ... < last */
+        long long done = 0;
+        LBM_TRY(lbm_converge(ctx, o->skip, o->THRESH, whole, df0, print_block, &bp, &done, &df));
+        t += done * o->skip;
+        converged = (done > 0 && df < o->THRESH);
+    }
+    while (!converged && t <= last) {
         long long T = ((t + o->skip - 1) / o->skip) * o->skip; /* next check iteration */
-        const int final_block = (T >= last);
-        const long long stop_at = final_block ? last : T; /* last iteration of this block */
-        if (final_block) {
-            /* run up to iteration last-1, take the fields the reference would print if this block
-             * does not converge, then do the final iteration */
-            if (stop_at - t > 0) LBM_TRY(lbm_step(ctx, stop_at - t));
-            if (o->SAVETXT == 1) {
-                LBM_TRY(lbm_macrovars(ctx, w->u1, w->u2, w->u3, NULL, w->vmag));
-                fields_taken = 1;
-            }
-            LBM_TRY(lbm_step(ctx, 1));
-            if (T > last) { /* no residual check at the final iteration */
-                LBM_TRY(lbm_sync(ctx));
-                break;
-            }
-        } else {
-            LBM_TRY(lbm_step(ctx, T - t + 1));
+        const long long stop_at = T >= last ? last : T;
+        /* run up to iteration last-1, take the fields the reference would print if this block
+         * does not converge, then do the final iteration */
+        if (stop_at - t > 0) LBM_TRY(lbm_step(ctx, stop_at - t));
+        if (o->SAVETXT == 1) {
+            LBM_TRY(lbm_macrovars(ctx, w->u1, w->u2, w->u3, NULL, w->vmag));
+            fields_taken = 1;
+        }
+        LBM_TRY(lbm_step(ctx, 1));
+        if (T > last) { /* no residual check at the final iteration */
+            LBM_TRY(lbm_sync(ctx));
+            break;
         }
         LBM_TRY(lbm_residual(ctx, &df));
         df *= df0;
-        const double stop = now() - start;
-        if (root) {
-            printf("\nIteration %lld:\n", T);
-            printf("df/df0:\t%.3e\n", df);
-            printf("Time:\t%.3e s\n", stop);
-            printf("LUPS:\t%.3e s\n", cells * (double)o->skip / stop);
-            fflush(stdout);
-        }
-        start = now();
-        if (df < o->THRESH) { fields_taken = 0; break; } /* converged: the newest state is printed (3D:119-122) */
-        t = T + 1;
+        lbm_block_record r = {T, df, 0, 1};
+        print_block(&r, &bp);
+        if (df < o->THRESH) fields_taken = 0; /* converged: the newest state is printed (3D:119-122) */
+        break;
     }
 
     /* Output to text file, 3D:127 */

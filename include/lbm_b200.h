@@ -117,6 +117,25 @@ int lbm_timer_stop(lbm_ctx *c, float *ms);
  * polls the negative-feq flag (returns LBM_ERR_UNSTABLE if set; *out is still written). */
 int lbm_residual(lbm_ctx *c, double *out);
 
+/* Replaces the reference's convergence loop (3D:103-124): up to max_blocks blocks of `skip`
+ * iterations; after each block df = diff(f2, f1, NQ) * df0 is evaluated and the loop stops when
+ * df < thresh (3D:119-122), when a negative equilibrium was seen, or after max_blocks.  On one GPU
+ * (skip a multiple of 4) the WHOLE loop runs as one CUDA graph with a device-side while condition:
+ * the host does not synchronise with the GPU between the blocks; `on_block` is called on the calling
+ * thread for every finished block, in order, as its record arrives in mapped host memory (the place
+ * for the reference's printf block, 3D:113-117).  Otherwise (several GPUs, other skip, option
+ * "converge_on_device" = 0) the same loop runs with one lbm_residual per block.  *blocks_done blocks
+ * were executed; *df_last is the last df.  Returns LBM_ERR_UNSTABLE like lbm_residual. */
+typedef struct lbm_block_record {
+    long long iteration;   /* iteration index t of this block's residual check */
+    double df;             /* diff(f2, f1, NQ) * df0 */
+    int status;            /* LBM_OK or LBM_ERR_UNSTABLE */
+    int last;              /* 1: the loop ended with this block */
+} lbm_block_record;
+typedef void (*lbm_block_fn)(const lbm_block_record *rec, void *user);
+int lbm_converge(lbm_ctx *c, long long skip, double thresh, long long max_blocks, double df0, lbm_block_fn on_block,
+                 void *user, long long *blocks_done, double *df_last);
+
 /* Direct access to the reference's `f2` (the distributions after the last iteration, post-BC,
  * pre-collision): writes this rank's planes into a FULL array of Q*cells_global doubles in the
  * reference's LU4 order (3D:48: q*N^3 + k*N^2 + j*N + i); other ranks' planes are untouched. */

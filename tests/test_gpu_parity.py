@@ -260,3 +260,60 @@ def test_cuda_graph_replay_gives_the_same_bits(lbm, oracle):
         sim.set_option("graphs", 1)
         sim.step(400)
         assert np.array_equal(bits(sim.f()), bits(o.f()))
+
+
+@pytest.mark.parametrize("cfg,skip", [(dict(N=20, Re=100), 100), (dict(N=16, Re=60, DIAG=1), 40), (dict(N=131, Re=300), 8)],
+                         ids=["N20", "N16diag", "N131pairs"])
+def test_device_side_convergence_loop_equals_the_host_loop(lbm, cfg, skip):
+    """lbm_converge: the whole convergence loop (main.c:103-124) as one conditional CUDA graph with the
+    `df < THRESH` test on the device must run the same blocks, report the same residuals and leave the
+    same distributions as the block-by-block host loop (option converge_on_device = 0)."""
+    out = []
+    for on_device in (1, 0):
+        with lbm.Cavity3D(**cfg) as sim:
+            sim.set_option("converge_on_device", on_device)
+            sim.step(1)
+            df0 = 1.0 / sim.residual()
+            seen = []
+            done, df, recs = sim.converge(skip, 1e-3 if cfg["N"] < 100 else 0.0, 30 if cfg["N"] < 100 else 3, df0,
+                                          lambda t, d: seen.append(t))
+            assert seen == [t for t, _ in recs] == [skip * (k + 1) for k in range(done)]
+            assert sim.info()["steps_done"] == 1 + done * skip
+            r = sim.residual()
+            assert r * df0 == pytest.approx(df, rel=1e-15)
+            # the loop can be continued: phase bookkeeping survives the graph
+            sim.step(3)
+            out.append((done, recs, sim.f()))
+    assert out[0][0] == out[1][0] and 1 <= out[0][0]
+    if cfg["N"] < 100 and out[0][0] < 30:                                            # stopped by the threshold, not by max_blocks
+        assert out[0][1][-1][1] < 1e-3 and all(d >= 1e-3 for _, d in out[0][1][:-1])
+    assert out[0][1] == out[1][1]                                                    # identical (iteration, df) records
+    assert np.array_equal(bits(out[0][2]), bits(out[1][2]))
+
+
+def test_device_side_convergence_loop_reports_instability(lbm):
+    with lbm.Cavity3D(N=12, Re=100, METHOD=0) as sim:
+        sim.step(1)
+        df0 = 1.0 / sim.residual()
+        with pytest.raises(lbm.UnstableError):
+            sim.converge(100, 1e-12, 50, df0)
+
+
+def test_short_horizon_parity_at_512(lbm, oracle):
+    """BASELINE configs[2] grid on one GPU against the 64-bit oracle (the reference's own `int` indexing
+    cannot run N >= 484): 6 iterations = 2 fused pairs + 2 single iterations, compared
+    through the macroscopic fields (bit-exact, 5 GB instead of 40 GB of host traffic) and the residual."""
+    cfg = dict(N=512, Re=1000)
+    o = oracle.Oracle3D(threads=0, **cfg)
+    o.step(6)
+    mo = o.macrovars()
+    want = o.last_diff
+    o.close()
+    with lbm.Cavity3D(**cfg) as sim:
+        assert sim.info()["pair_enabled"] == 1
+        sim.step(6)
+        r = sim.residual()
+        mg = sim.macrovars()
+    assert r == pytest.approx(want, rel=RESID_RTOL)
+    for k in ("rho", "u1", "u2", "u3", "vmag"):
+        assert np.array_equal(bits(mg[k]), bits(mo[k])), k

@@ -91,3 +91,10 @@ def test_large_grid_properties(lbm):
         assert np.array_equal(bits(ma["u"]), bits(mb["u"])) and np.array_equal(bits(ma["rho"]), bits(mb["rho"]))
         assert np.isfinite(ma["rho"]).all() and abs(ma["rho"].mean() - 1.0) < 1e-6
         assert ma["u"].reshape(N, N)[N - 1].min() > 0.0
+
+
+def test_vmag_is_computed_on_the_device(lbm):
+    with lbm.Cavity2D(N=33, M=47, Re=40.0) as sim:
+        sim.step(60)
+        mv = sim.macro()
+    assert np.array_equal(mv["vmag"], np.sqrt(mv["u"] * mv["u"] + mv["v"] * mv["v"])) and mv["vmag"].max() > 0.01

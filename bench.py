@@ -512,6 +512,12 @@ def main():
     if not a.no_e2e:
         sim.set_option("host_local_layout", 1)
         nloc = info0["cells_local"]
+        # several ranks: allocate the pinned buffers on the GPU's own NUMA node (PCIe traffic of 8 ranks
+        # otherwise crosses the socket interconnect); undone before the CPU baseline uses all cores
+        old_affinity = None
+        if multi:
+            import cfd_codes_b200.distributed as D
+            old_affinity = D.bind_to_gpu_numa(local_rank)
         h_f = torch.empty(19 * nloc, dtype=torch.float64, pin_memory=True)
         h_mv = [[torch.empty(nloc, dtype=torch.float64, pin_memory=True) for _ in range(5)] for _ in range(2)]
         sim._L.lbm_get_f(sim._h, h_f.data_ptr())       # a valid state to restart from
@@ -555,6 +561,9 @@ def main():
                "serial": {"value": cells * block / dt_serial / 1e6, "unit": "MLUPS", "ms_per_step": dt_serial * 1e3,
                           "call": "lbm_set_f + lbm_step(%d) + lbm_residual + lbm_macrovars, nothing overlapped" % block}}
         del h_f, h_mv
+        if old_affinity is not None:
+            os.sched_setaffinity(0, old_affinity)
+        e2e["numa_bound"] = old_affinity is not None
     sim.close()
 
     if multi:

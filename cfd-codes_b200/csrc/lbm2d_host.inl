@@ -35,6 +35,7 @@ static int block2d(const lbm_ctx *c) {
 }
 
 static int halo_exchange2d(lbm_ctx *c, double *L, cudaStream_t st) {
+    if (c->slab_emulation) return LBM_OK;
     const int r = c->prm.rank, P = c->prm.nranks;
     const size_t n = (size_t)c->N;
     NK(g_nccl.GroupStart());

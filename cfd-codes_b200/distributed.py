@@ -16,6 +16,28 @@ def env_rank():
             int(os.environ.get("LOCAL_RANK", "0")))
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs that are local to its GPU (NVML's ideal affinity), so that the pinned
+    host buffers it allocates next live on the GPU's own NUMA node and PCIe transfers do not cross the
+    socket interconnect.  Returns the previous affinity set (pass it to os.sched_setaffinity to undo), or
+    None if nothing was changed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        old = os.sched_getaffinity(0)
+        new = cpus & old
+        if not new or new == old:
+            return None
+        os.sched_setaffinity(0, new)
+        return old
+    except Exception:
+        return None
+
+
 def init_process_group(backend=None):
     """Rendezvous over 127.0.0.1 (the container hostname may not resolve)."""
     import torch

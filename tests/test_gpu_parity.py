@@ -314,6 +314,8 @@ def test_short_horizon_parity_at_512(lbm, oracle):
         sim.step(6)
         r = sim.residual()
         mg = sim.macrovars()
-    assert r == pytest.approx(want, rel=RESID_RTOL)
     for k in ("rho", "u1", "u2", "u3", "vmag"):
         assert np.array_equal(bits(mg[k]), bits(mo[k])), k
+    # sum of 2.5e9 squares: the two summation orders (neither is the reference's, which leaves its own
+    # unspecified, main.c:680) differ by ~sqrt(n) * eps = 6e-12 relative; the FIELD is the bit-exact part
+    assert r == pytest.approx(want, rel=1e-10)

@@ -95,7 +95,7 @@ if a.mode == "big512":
         o.step(a.steps)
         mo = o.macrovars()
         same = {k: bool(np.array_equal(full[k].reshape(-1).view(np.uint64), mo[k].view(np.uint64))) for k in full}
-        res_ok = abs(res - o.last_diff) <= 1e-12 * abs(o.last_diff)
+        res_ok = abs(res - o.last_diff) <= 1e-10 * abs(o.last_diff)   # 2.5e9-term sums in two different orders
         ok = all(same.values()) and res_ok
         print(json.dumps({"world": world, "mode": "big512", "N": a.N, "steps": a.steps, "pair": int(pair_on), "fields_bit_equal": same,
                           "bit_equal": all(same.values()), "rho_equal": same["rho"], "residual_ok": bool(res_ok),

@@ -131,3 +131,35 @@ def test_step_kernel_memory_instructions(lbm):
     sec = [x for x in re.split(r"\n\s*Function : ", out) if x.startswith("_ZN5lbm3d6k_stepILi1ELi0ELb1ELb0EEEvNS_2KPE")][0]
     assert len(re.findall(r"\bLDG\.E\.64\b", sec)) == 20 and len(re.findall(r"\bSTG\.E\.64\b", sec)) == 20
     assert not re.findall(r"\b(LDL|STL)\b", sec)
+
+
+def _sass_section(lbm, prefix):
+    out = subprocess.run(["cuobjdump", "-sass", lbm.LIB_PATH], capture_output=True, text=True).stdout
+    sec = [x for x in re.split(r"\n\s*Function : ", out) if x.startswith(prefix)]
+    assert len(sec) == 1, prefix
+    return sec[0]
+
+
+def test_pair_kernel_memory_instructions_and_no_fma(lbm):
+    """k_step_pair (two iterations per pass), default variant (32 x 10 threads, two blocks per SM, direct
+    pulls): one load and one store per population for TWO updates of a cell -- 19 LDG + the two stale-f14
+    side loads, 19 STG + the two side stores -- the intermediate time level goes through shared memory
+    (16 STS.64 / 16 LDS.64, two barriers per plane), and -fmad=false holds (DFMA only inside 1.0/rho)."""
+    sec = _sass_section(lbm, "_ZN5lbm3d11k_step_pairILi1ELb1ELi10ELi2ELi3E")
+    n = {k: len(re.findall(r"\b%s\b" % k, sec)) for k in (r"LDG\.E\.64", r"STG\.E\.64", r"LDS\.64", r"STS\.64", r"BAR\.SYNC", "DFMA", "DADD", "DMUL")}
+    assert n[r"LDG\.E\.64"] == 21 and n[r"STG\.E\.64"] == 21, n
+    assert n[r"LDS\.64"] == 16 and n[r"STS\.64"] == 16 and n[r"BAR\.SYNC"] == 2, n
+    assert n["DFMA"] <= 24 and n["DADD"] > 300 and n["DMUL"] > 160, n
+    out = subprocess.run(["cuobjdump", "-res-usage", lbm.LIB_PATH], capture_output=True, text=True).stdout
+    m = re.search(r"Function _ZN5lbm3d11k_step_pairILi1ELb1ELi10ELi2ELi3EEEvNS_2KPE14CUtensorMap_st:\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    assert m and int(m.group(1)) <= 102 and int(m.group(2)) <= 16, m and m.groups()   # 2 blocks x 320 threads per SM
+
+
+def test_tma_variants_use_the_tma_unit(lbm):
+    """The TMA-staged variants pull S(t) with tensor copies: 19 UTMALDG.4D at the prologue + 19 in the
+    loop, completion on an mbarrier (SYNCS), and no per-thread global loads except the side buffer."""
+    for prefix in ("_ZN5lbm3d11k_step_pairILi1ELb1ELi16ELi1ELi4E", "_ZN5lbm3d11k_step_pairILi1ELb1ELi8ELi2ELi4E"):
+        sec = _sass_section(lbm, prefix)
+        assert len(re.findall(r"\bUTMALDG\.4D\b", sec)) == 38, prefix
+        assert len(re.findall(r"\bSYNCS\.PHASECHK\.TRANS64\.TRYWAIT\b", sec)) >= 1
+        assert len(re.findall(r"\bLDG\.E\.64\b", sec)) == 2 and len(re.findall(r"\bSTG\.E\.64\b", sec)) == 21

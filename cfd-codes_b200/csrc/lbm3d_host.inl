@@ -211,13 +211,16 @@ static int launch_pair(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, cudaStream_t s
     }
 }
 
+// Every rank must come to the same answer (the halo depth depends on it), so the test uses only
+// rank-independent quantities: the smallest slab of the decomposition and the average slab size.
 static bool pair_enabled(const lbm_ctx *c) {
     if (c->prm.dim != 3) return false;
-    if (c->prm.nranks > 1 && (c->p2p || c->nzl < 4 || c->G < 2)) return false;   // the fused direct halo is single-step only
+    const int P = c->prm.nranks;
+    if (P > 1 && (c->p2p || c->N / P < 4 || c->G < 2)) return false;   // the fused direct halo is single-step only
     if (c->pair >= 0) return c->pair != 0;
-    // automatic: HBM-resident slabs (>= 128^3 cells per GPU); below that the step is launch-bound and
-    // the CUDA-graph / direct-halo paths of the single-step kernel win
-    return c->FS >= (1LL << 21);
+    // automatic: HBM-resident slabs (>= 128^3 cells per GPU on average); below that the step is
+    // launch-bound and the CUDA-graph / direct-halo paths of the single-step kernel win
+    return (c->N2 * c->N) / P >= (1LL << 21);
 }
 
 // Iterations t = steps and t+1 in ONE pass: reads lat[cur] = S(t-1), writes lat[cur^1] = S(t+1).

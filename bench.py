@@ -492,13 +492,16 @@ def main():
     n_k = i1["plain_step_iterations"] - i0["plain_step_iterations"]
     ms_k = allmax(i1["plain_step_ms"] - i0["plain_step_ms"])
     pair_on = bool(i1.get("pair_enabled", 0))
+    pair_tma = pair_on and i1.get("pair_variant", -1) in (8, 9, 10)
     upd = 2 if pair_on else 1
     peak, peak_src = peaks()
     cells_per_launch = cells / world  # per GPU: its slab
     achieved = B_ALG * cells_per_launch / (ms_k * 1e-3 / n_k) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic("%d/%d%s" % (N, world, "/pair" if pair_on else "")),
-                "kernel": "lbm3d::k_step_pair<TRT> (two iterations per pass)" if pair_on else "lbm3d::k_step<TRT, MODE_STEP>",
+                "traffic": ncu_traffic("%d/%d%s" % (N, world, ("/pair_tma" if pair_tma else "/pair") if pair_on else "")),
+                "kernel": ("lbm3d::k_step_pair<TRT> (two iterations per pass, variant %d: %s)" % (
+                    i1.get("pair_variant", -1), "TMA-staged pulls, UTMALDG.4D" if pair_tma else "direct pulls")) if pair_on
+                else "lbm3d::k_step<TRT, MODE_STEP>",
                 "peak_source": peak_src, "updates_per_launch": upd,
                 "algorithmic_bytes_per_launch": B_ALG * cells_per_launch * upd, "launch_ms": ms_k / n_k * upd,
                 "launches_timed": int(n_k // upd), "timed_with": "CUDA events around the plain-iteration batches inside the timed region",

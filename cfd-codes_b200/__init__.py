@@ -56,7 +56,7 @@ class LbmInfo(C.Structure):
         ("Q", C.c_int), ("k0", C.c_int), ("k1", C.c_int), ("cells_local", C.c_longlong),
         ("cells_global", C.c_longlong), ("steps_done", C.c_longlong), ("kernel_launches", C.c_longlong),
         ("device_bytes", C.c_longlong), ("plain_step_ms", C.c_double), ("plain_step_iterations", C.c_longlong),
-        ("pair_enabled", C.c_int),
+        ("pair_enabled", C.c_int), ("pair_variant", C.c_int),
     ]
 
 

@@ -154,11 +154,20 @@ static int launch_pair_v(lbm_ctx *c, const lbm3d::KP &p, dim3 grid, cudaStream_t
 struct PairVariant { int ty, minb, stage; };
 static const PairVariant PAIR_VARIANTS[] = {{20, 1, 0}, {16, 1, 2}, {10, 2, 0}, {16, 1, 0}, {16, 1, 1}, {17, 1, 1}, {12, 1, 1}, {10, 2, 3}, {16, 1, 4}, {8, 2, 4}, {12, 1, 4}};
 static const int PAIR_NVARIANTS = (int)(sizeof(PAIR_VARIANTS) / sizeof(PAIR_VARIANTS[0]));
-static const int PAIR_DEFAULT_VARIANT = 7;   // 2 blocks of 32 x 10 per SM, no prefetch: best of profiles/r02_pair_ab.md
+// Defaults (profiles/r02_summary.md): 7 = two blocks of 32 x 10 per SM with direct pulls -- no restriction
+// on N, best at 256^3 and on slabs; 8 = the TMA-staged 32 x 16 block with 64-plane segments for one big
+// even-N grid per GPU (>= 2^26 cells: enough blocks to hide its one-block-per-SM wave quantisation), where
+// it measured 1 % faster with 11 % fewer instructions.
+static const int PAIR_VARIANT_DIRECT = 7, PAIR_VARIANT_TMA = 8;
+
+static int pair_variant_requested(const lbm_ctx *c) {
+    if (c->pair_variant >= 0 && c->pair_variant < PAIR_NVARIANTS) return c->pair_variant;
+    return (c->prm.nranks == 1 && (c->N % 2) == 0 && c->N2 * c->N >= (1LL << 26)) ? PAIR_VARIANT_TMA : PAIR_VARIANT_DIRECT;
+}
 
 static int pair_variant(const lbm_ctx *c) {
-    int v = (c->pair_variant >= 0 && c->pair_variant < PAIR_NVARIANTS) ? c->pair_variant : PAIR_DEFAULT_VARIANT;
-    if (PAIR_VARIANTS[v].stage == 4 && !c->tmap_ok) v = 7;   // TMA needs 16-byte strides (N even)
+    int v = pair_variant_requested(c);
+    if (PAIR_VARIANTS[v].stage == 4 && !c->tmap_ok) v = PAIR_VARIANT_DIRECT;   // TMA needs 16-byte strides (N even)
     return v;
 }
 
@@ -178,7 +187,7 @@ static int make_tensor_maps(lbm_ctx *c) {
         cudaGetLastError();
         return LBM_OK;   // no TMA variants; everything else works
     }
-    const int ty = PAIR_VARIANTS[(c->pair_variant >= 0 && c->pair_variant < PAIR_NVARIANTS) ? c->pair_variant : PAIR_DEFAULT_VARIANT].ty;
+    const int ty = PAIR_VARIANTS[pair_variant_requested(c)].ty;
     for (int l = 0; l < 2; l++) {
         const cuuint64_t dims[4] = {(cuuint64_t)c->N, (cuuint64_t)c->N, (cuuint64_t)(c->nzl + 2 * c->G), (cuuint64_t)lbm3d::Q};
         const cuuint64_t strides[3] = {(cuuint64_t)c->N * 8, (cuuint64_t)c->N2 * 8, (cuuint64_t)c->PS * 8};
@@ -234,7 +243,7 @@ static int run_pair(lbm_ctx *c) {
     if (PAIR_VARIANTS[pair_variant(c)].stage == 4 && c->tmap_ty != pair_ty(c)) make_tensor_maps(c);
     const int ty = pair_ty(c);
     const unsigned gx = (c->N + lbm3d::PAIR_OX - 1) / lbm3d::PAIR_OX, gy = (c->N + ty - 3) / (ty - 2);
-    int Lz = c->pair_lz > 0 ? c->pair_lz : 32;
+    int Lz = c->pair_lz > 0 ? c->pair_lz : (pair_variant(c) == PAIR_VARIANT_TMA ? 64 : 32);
     int rc;
     if (c->prm.nranks == 1) {
         p.zlo = 0; p.zhi = c->nzl;

@@ -684,6 +684,7 @@ int lbm_get_info(lbm_ctx *c, lbm_info *o) {
     resolve_spans(c, true);
     o->plain_step_ms = c->plain_ms; o->plain_step_iterations = c->plain_iters;
     o->pair_enabled = (c->prm.dim == 3 && pair_enabled(c)) ? 1 : 0;
+    o->pair_variant = c->prm.dim == 3 ? pair_variant(c) : -1;
     return LBM_OK;
 }
 

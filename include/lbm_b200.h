@@ -74,6 +74,7 @@ typedef struct lbm_info {
                                      iterations run by the plain step kernel inside lbm_step (dim=3) ... */
     long long plain_step_iterations; /* ... and how many iterations that covers */
     int pair_enabled;             /* 1: plain iterations run two per pass over HBM (csrc/lbm3d_pair.cuh) */
+    int pair_variant;             /* ... with this tile variant (7 = direct pulls, 8/9/10 = TMA-staged) */
 } lbm_info;
 
 /* Fills *p with the reference's defaults: dim=3, N=50, Re=100, UMAX=0.1, METHOD=1 (TRT), GAMMA=1,

@@ -20,8 +20,8 @@
 // redundantly by the neighbouring blocks -- no communication between blocks, no global intermediate.
 //
 // Shared memory per thread-cell: up-going {9,11,16,18} x 3 planes, in-plane {1,2,3,4,7,8,13,14} x 2
-// planes, down-going {10,12,15,17} x 1 plane = 32 doubles = 256 B  (TY = 18: 147 456 B per block,
-// one block per SM).  Populations 0, 5, 6 never leave the thread.
+// planes, down-going {10,12,15,17} x 1 plane = 32 doubles = 256 B  (TY = 10: 81 920 B per block, two
+// blocks per SM; the staged variants add 152 B per cell).  Populations 0, 5, 6 never leave the thread.
 //
 // Stale f14 (3D:421): iteration t reads slot (t+2)%4 of the `side` history and writes slot t%4, so
 // the two fused iterations read {t+2, t+3} and write {t, t+1} (mod 4): redundant step-A work in
@@ -46,7 +46,7 @@ __host__ __device__ constexpr int pair_smem_bytes(int TY, int STAGE) {
 
 #define LBM_PREFETCH_L2(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))
 
-// Variants (template parameters, A/B'd on the GPU, profiles/r02_pair_ab.md):
+// Variants (template parameters, A/B'd on the GPU: profiles/r02_summary.md):
 //   MINB  resident blocks per SM the register budget is sized for (1: big tiles; 2: two smaller blocks
 //         whose load and compute phases interleave);
 //   STAGE 0: step A pulls straight from HBM/L2 into registers (L2 prefetch one plane ahead);
@@ -61,9 +61,10 @@ __host__ __device__ constexpr int pair_smem_bytes(int TY, int STAGE) {
 //            even column 30*bx - 2 and is two columns wider than the tile; the x shift -cx is applied
 //            when the thread reads its value back.  Needs N even (16-byte row stride);
 //         2: like 0 but software-pipelined through 19 extra registers (slower: 128 registers leave
-//            16 warps per SM and the pulls still stall -- kept for the record, profiles/r02_pair_ab.md).
+//            16 warps per SM and the pulls still stall -- kept for the record);
+//         3: 0 without the L2 prefetch (the 19 prefetch instructions per thread cost more than they save).
 //
-// grid = (ceil(N/30), ceil(N/(TY-2)), ceil((zhi-zlo)/Lz)); block = (32, TY); dynamic smem = pair_smem_bytes(TY).
+// grid = (ceil(N/30), ceil(N/(TY-2)), z segments); block = (32, TY); dynamic smem = pair_smem_bytes(TY, STAGE).
 template <int METHOD, bool G1, int TY, int MINB, int STAGE>
 __global__ void __launch_bounds__(PAIR_TX *TY, MINB) k_step_pair(const __grid_constant__ KP p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) double sm[];

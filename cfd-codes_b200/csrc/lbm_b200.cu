@@ -30,7 +30,7 @@ extern "C" {
 
 const char *lbm_last_error(void) { return g_err; }
 
-const char *lbm_version(void) { return "lbm_b200 0.1 (sm_100a, fp64, -fmad=false, D3Q19 pull/two-lattice)"; }
+const char *lbm_version(void) { return "lbm_b200 0.2 (sm_100a, fp64, -fmad=false, D3Q19 pull/two-lattice, two iterations per pass)"; }
 
 void lbm_default_params(lbm_params *p) {
     memset(p, 0, sizeof(*p));

@@ -32,3 +32,16 @@ def test_reference_arm_falls_back_to_the_oracle_port_for_unbuilt_grids():
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     assert run_ref("--gpus", "2", "--grid", "20", env=env) == []
+
+
+def test_both_arms_use_the_same_workload_label():
+    """The driver compares config.workload of the two arms (same_config): one function builds both."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    j = json.loads(run_ref("--grid", "24", "--Re", "100")[-1])
+    assert j["config"]["workload"] == bench.workload_label(24, 100, 1)
+    j = json.loads(run_ref("--grid", "20", "--Re", "77", "--gpus", "4")[-1])
+    assert j["config"]["workload"] == bench.workload_label(20, 77, 4) and j["n_gpus"] == 4
+    assert j["config"]["cpu_code"] == "port" and j["cpu_baseline"]["kind"] == "port"
